@@ -1,0 +1,37 @@
+# Build of the B200 POTRF engine (sm_100a only), its C-ABI shared library and test tools.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Iinclude
+CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -Iinclude -I/usr/local/cuda/include
+CSRC      := dla-future_b200/csrc
+LIBDIR    := dla-future_b200/lib
+LIB       := $(LIBDIR)/libdlaf_b200.so
+
+CU_OBJS  := build/gemm_dmma.o build/potrf_tile.o build/layout.o build/engine.o
+CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
+OBJS     := $(CU_OBJS) $(CPP_OBJS)
+HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h)
+
+all: $(LIB) tools/gpu_kernel_test
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+build/%.o: $(CSRC)/%.cpp $(HDRS)
+	@mkdir -p build
+	g++ $(CXXFLAGS) -c $< -o $@
+
+# cudart is linked statically (nvcc default) so the library does not depend on which libcudart the
+# host process (e.g. torch) has loaded; NCCL is the system libnccl.so.2.
+$(LIB): $(OBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lnccl -lpthread
+
+tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_tile.o $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/potrf_tile.o -lcublas -o $@
+
+clean:
+	rm -rf build tools/gpu_kernel_test $(LIBDIR)/*.so
+
+.PHONY: all clean

@@ -1,0 +1,506 @@
+// C ABI of the B200 POTRF path — the drop-in boundary (include/dlaf_c/*.h).
+// Reference counterparts: src/c_api/init.cpp:19-50, src/c_api/grid.cpp:26-96, src/c_api/utils.cpp:26-69,
+// src/c_api/factorization/cholesky.h:32-73 and cholesky.cpp:19-48.
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+
+#include <dlaf_c/b200_ext.h>
+#include <dlaf_c/factorization/cholesky.h>
+#include <dlaf_c/grid.h>
+#include <dlaf_c/init.h>
+
+#include "comm.h"
+#include "common.h"
+#include "engine.h"
+#include "util_matrix.h"
+
+using namespace dlaf_b200;
+
+namespace {
+
+struct EngineKey {
+  long n = -1;
+  int nb = 0, isrc = 0, jsrc = 0, transposed = 0;
+  bool operator==(const EngineKey& o) const {
+    return n == o.n && nb == o.nb && isrc == o.isrc && jsrc == o.jsrc && transposed == o.transposed;
+  }
+};
+
+struct EngineSlotBase {
+  virtual ~EngineSlotBase() = default;
+  virtual int info(cudaStream_t s) = 0;
+  virtual long launches() const = 0;
+};
+
+template <class D>
+struct EngineSlot : EngineSlotBase {
+  EngineKey key;
+  std::unique_ptr<PotrfEngine<D>> eng;
+  D* stage = nullptr;  // device copy of the user's local part, in the user's layout
+  size_t stage_elems = 0;
+  ~EngineSlot() override { cudaFree(stage); }
+  int info(cudaStream_t s) override { return eng ? eng->info(s) : 0; }
+  long launches() const override { return eng ? eng->launches() : 0; }
+  D* ensure_stage(size_t elems) {
+    if (elems > stage_elems) {
+      cudaFree(stage);
+      DLAF_CUDA_CHECK(cudaMalloc(&stage, sizeof(D) * elems));
+      stage_elems = elems;
+    }
+    return stage;
+  }
+};
+
+struct GridCtx {
+  std::unique_ptr<CommGrid> grid;
+  std::unique_ptr<EngineSlotBase> slot[4];  // s, d, c, z
+  int last_type = -1;
+  cudaStream_t stream = nullptr;  // stream of the synchronous host API
+  int* d_red = nullptr;           // info reduction buffer
+  ~GridCtx() {
+    for (auto& s : slot)
+      s.reset();
+    if (stream)
+      cudaStreamDestroy(stream);
+    cudaFree(d_red);
+  }
+};
+
+std::map<int, std::unique_ptr<GridCtx>> g_grids;  // unsynchronised like src/c_api/grid.cpp:26
+int g_next_ctx = INT_MAX;
+bool g_initialized = false;
+int g_device = -1;
+
+template <class T>
+struct TypeIndex;
+template <>
+struct TypeIndex<float> {
+  static constexpr int value = 0;
+};
+template <>
+struct TypeIndex<double> {
+  static constexpr int value = 1;
+};
+template <>
+struct TypeIndex<std::complex<float>> {
+  static constexpr int value = 2;
+};
+template <>
+struct TypeIndex<std::complex<double>> {
+  static constexpr int value = 3;
+};
+
+void ensure_initialized() {
+  if (!g_initialized)
+    dlaf_initialize(0, nullptr, 0, nullptr);
+}
+
+GridCtx& grid_from_context(int ctx) {
+  auto it = g_grids.find(ctx);
+  if (it == g_grids.end()) {
+    // src/c_api/utils.cpp:56-69
+    std::fprintf(stderr, "[ERROR] No DLA-Future grid for context %d. Did you forget to call dlaf_create_grid?\n",
+                 ctx);
+    std::fflush(stderr);
+    std::terminate();
+  }
+  return *it->second;
+}
+
+inline int cnt_tiles(long g_end, int r, int grid) {
+  return g_end > r ? static_cast<int>((g_end - r + grid - 1) / grid) : 0;
+}
+
+struct UserGeom {
+  long n;
+  int nb, nt;
+  int P, Q, vrow, vcol;  // virtual (source-adjusted) coordinates in the user's grid
+  long lrows, lcols;     // local size
+  int ltr, ltc;
+};
+
+UserGeom user_geometry(const CommGrid& g, const DLAF_descriptor& d) {
+  // same preconditions as the reference (factorization/cholesky.h:43-46, src/c_api/factorization/cholesky.h:36-38)
+  DLAF_B200_ASSERT(d.m == d.n, "matrix must be square");
+  DLAF_B200_ASSERT(d.mb == d.nb && d.nb >= 1, "blocks must be square");
+  DLAF_B200_ASSERT(d.i == 0 && d.j == 0, "sub-matrix offsets must be 0");
+  DLAF_B200_ASSERT(d.isrc >= 0 && d.isrc < g.P && d.jsrc >= 0 && d.jsrc < g.Q, "source rank");
+  UserGeom u;
+  u.n = d.n;
+  u.nb = d.nb;
+  u.nt = ceil_div(u.n, u.nb);
+  u.P = g.P;
+  u.Q = g.Q;
+  u.vrow = (g.row - d.isrc + g.P) % g.P;
+  u.vcol = (g.col - d.jsrc + g.Q) % g.Q;
+  u.ltr = cnt_tiles(u.nt, u.vrow, u.P);
+  u.ltc = cnt_tiles(u.nt, u.vcol, u.Q);
+  auto lsize = [&](int lt, int v, int grid) {
+    long s = static_cast<long>(lt) * u.nb;
+    if (u.nt > 0 && (u.nt - 1) % grid == v)
+      s -= static_cast<long>(u.nt) * u.nb - u.n;  // the ragged last tile is mine
+    return s;
+  };
+  u.lrows = lsize(u.ltr, u.vrow, u.P);
+  u.lcols = lsize(u.ltc, u.vcol, u.Q);
+  return u;
+}
+
+bool is_upper(char uplo) {
+  DLAF_B200_ASSERT(uplo == 'L' || uplo == 'l' || uplo == 'U' || uplo == 'u', "uplo must be L or U");
+  return uplo == 'U' || uplo == 'u';
+}
+
+template <class T>
+EngineSlot<devtype_t<T>>& get_engine(GridCtx& c, const DLAF_descriptor& d, const UserGeom& u, bool upper) {
+  using D = devtype_t<T>;
+  constexpr int ti = TypeIndex<T>::value;
+  if (!c.slot[ti])
+    c.slot[ti].reset(new EngineSlot<D>);
+  auto& slot = static_cast<EngineSlot<D>&>(*c.slot[ti]);
+  EngineKey key;
+  key.n = u.n;
+  key.nb = u.nb;
+  key.isrc = d.isrc;
+  key.jsrc = d.jsrc;
+  key.transposed = upper ? 1 : 0;
+  if (!slot.eng || !(slot.key == key)) {
+    slot.eng.reset();
+    EngineGeometry g;
+    g.n = u.n;
+    g.nb = u.nb;
+    const CommGrid& cg = *c.grid;
+    if (!upper) {
+      g.P = u.P;
+      g.Q = u.Q;
+      g.prow = u.vrow;
+      g.pcol = u.vcol;
+      g.src_in_col_comm = d.isrc;
+      g.src_in_row_comm = d.jsrc;
+      slot.eng.reset(new PotrfEngine<D>(g, cg.row_comm, cg.col_comm));
+    }
+    else {
+      // U = (lower factor of the conjugate-transposed problem)^H on the transposed grid: the engine's
+      // process rows are the user's process columns and vice versa (layout.cuh).
+      g.P = u.Q;
+      g.Q = u.P;
+      g.prow = u.vcol;
+      g.pcol = u.vrow;
+      g.src_in_col_comm = d.jsrc;
+      g.src_in_row_comm = d.isrc;
+      slot.eng.reset(new PotrfEngine<D>(g, cg.col_comm, cg.row_comm));
+    }
+    slot.key = key;
+  }
+  c.last_type = ti;
+  return slot;
+}
+
+// Copies the referenced triangle between the user's host matrix and a device buffer with the same
+// tile structure (tile edge `tile` on the device side, nb on the host side are equal here), one
+// 2D copy per local tile column.
+template <class D>
+void copy_triangle(bool to_device, bool upper, const UserGeom& u, D* host, long ldh, D* dev, long ldd,
+                   cudaStream_t s) {
+  for (int lj = 0; lj < u.ltc; ++lj) {
+    const long gj = static_cast<long>(lj) * u.Q + u.vcol;
+    const long c0 = static_cast<long>(lj) * u.nb;
+    const long width = std::min<long>(u.nb, u.lcols - c0);
+    long r0, r1;
+    if (!upper) {
+      r0 = static_cast<long>(cnt_tiles(gj, u.vrow, u.P)) * u.nb;  // first local row tile with gi >= gj
+      r1 = u.lrows;
+    }
+    else {
+      r0 = 0;
+      r1 = std::min<long>(u.lrows, static_cast<long>(cnt_tiles(gj + 1, u.vrow, u.P)) * u.nb);
+    }
+    if (r1 <= r0 || width <= 0)
+      continue;
+    D* h = host + r0 + c0 * ldh;
+    D* d = dev + r0 + c0 * ldd;
+    if (to_device)
+      DLAF_CUDA_CHECK(cudaMemcpy2DAsync(d, sizeof(D) * ldd, h, sizeof(D) * ldh, sizeof(D) * (r1 - r0), width,
+                                        cudaMemcpyHostToDevice, s));
+    else
+      DLAF_CUDA_CHECK(cudaMemcpy2DAsync(h, sizeof(D) * ldh, d, sizeof(D) * ldd, sizeof(D) * (r1 - r0), width,
+                                        cudaMemcpyDeviceToHost, s));
+  }
+}
+
+int reduce_info(GridCtx& c, int info, cudaStream_t s) {
+  CommGrid& g = *c.grid;
+  if (g.P * g.Q == 1 || g.grid_comm == nullptr)
+    return info;
+  if (!c.d_red)
+    DLAF_CUDA_CHECK(cudaMalloc(&c.d_red, sizeof(int)));
+  DLAF_CUDA_CHECK(cudaMemcpyAsync(c.d_red, &info, sizeof(int), cudaMemcpyHostToDevice, s));
+  DLAF_NCCL_CHECK(ncclAllReduce(c.d_red, c.d_red, 1, ncclInt32, ncclMax, g.grid_comm, s));
+  DLAF_CUDA_CHECK(cudaMemcpyAsync(&info, c.d_red, sizeof(int), cudaMemcpyDeviceToHost, s));
+  DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+  return info;
+}
+
+// Host entry point: H2D of the referenced triangle, factorization, D2H (the reference's MatrixMirror
+// bracket, src/c_api/factorization/cholesky.h:48-53, moves the whole local matrix both ways).
+template <class T>
+int cholesky_host(int ctx, char uplo, T* a, const DLAF_descriptor& desc) {
+  using D = devtype_t<T>;
+  ensure_initialized();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return 0;
+  const bool upper = is_upper(uplo);
+  const UserGeom u = user_geometry(*c.grid, desc);
+  DLAF_B200_ASSERT(desc.ld >= std::max<long>(1, u.lrows), "leading dimension smaller than local rows");
+  auto& slot = get_engine<T>(c, desc, u, upper);
+  PotrfEngine<D>& eng = *slot.eng;
+  eng.unbind_external();
+  D* host = reinterpret_cast<D*>(a);
+  cudaStream_t s = c.stream;
+  if (u.n > 0 && u.lrows > 0 && u.lcols > 0) {
+    if (!upper && !eng.padded()) {
+      // tiles need no padding: the slab IS the user layout, copy straight into it
+      D* slab = eng.slab();
+      copy_triangle<D>(true, false, u, host, desc.ld, slab, eng.slab_ld(), s);
+      eng.factorize(s);
+      copy_triangle<D>(false, false, u, host, desc.ld, slab, eng.slab_ld(), s);
+    }
+    else {
+      const long lds = round_up(u.lrows, 2);
+      D* stage = slot.ensure_stage(static_cast<size_t>(lds) * u.lcols);
+      copy_triangle<D>(true, upper, u, host, desc.ld, stage, lds, s);
+      eng.load(stage, lds, upper, s);
+      eng.factorize(s);
+      eng.store(stage, lds, upper, s);
+      copy_triangle<D>(false, upper, u, host, desc.ld, stage, lds, s);
+    }
+  }
+  else {
+    eng.factorize(s);  // still takes part in the collectives of the grid
+  }
+  const int info = eng.info(s);
+  return reduce_info(c, info, s);
+}
+
+template <class T>
+int cholesky_device(int ctx, char uplo, T* a_dev, const DLAF_descriptor& desc, void* stream) {
+  using D = devtype_t<T>;
+  ensure_initialized();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return 0;
+  const bool upper = is_upper(uplo);
+  const UserGeom u = user_geometry(*c.grid, desc);
+  auto& slot = get_engine<T>(c, desc, u, upper);
+  PotrfEngine<D>& eng = *slot.eng;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  D* dev = reinterpret_cast<D*>(a_dev);
+  EngineGeometry probe;
+  probe.n = u.n;
+  probe.nb = u.nb;
+  if (!upper && u.lrows > 0 && u.lcols > 0 && PotrfEngine<D>::can_run_in_place(probe, dev, desc.ld)) {
+    eng.bind_external(dev, desc.ld);
+    eng.factorize(s);
+  }
+  else {
+    eng.unbind_external();
+    if (u.lrows > 0 && u.lcols > 0)
+      eng.load(dev, desc.ld, upper, s);
+    eng.factorize(s);
+    if (u.lrows > 0 && u.lcols > 0)
+      eng.store(dev, desc.ld, upper, s);
+  }
+  return 0;
+}
+
+template <class T>
+void pxpotrf(char uplo, int n, T* a, int ia, int ja, const int desca[9], int* info) {
+  // src/c_api/factorization/cholesky.h:62-73
+  DLAF_B200_ASSERT(desca[0] == 1, "only dense descriptors (dtype 1)");
+  DLAF_B200_ASSERT(ia == 1 && ja == 1, "ia and ja must be 1");
+  const DLAF_descriptor d = make_dlaf_descriptor(n, n, ia, ja, desca);
+  const int r = cholesky_host<T>(desca[1], uplo, a, d);
+  if (info)
+    *info = r;
+}
+
+template <class T>
+void random_hpd(int ctx, T* a, const DLAF_descriptor& desc) {
+  ensure_initialized();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return;
+  const UserGeom u = user_geometry(*c.grid, desc);
+  LocalMatrixView<T> v{a, desc.ld, u.n, u.nb, u.P, u.Q, u.vrow, u.vcol};
+  set_random_hermitian_positive_definite_local<T>(v);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+void dlaf_initialize(int, const char**, int argc_dlaf, const char** argv_dlaf) noexcept {
+  if (g_initialized)
+    return;
+  int device = -1;
+  bool print_config = false;
+  if (const char* e = std::getenv("DLAF_B200_DEVICE"))
+    device = std::atoi(e);
+  else if (const char* e2 = std::getenv("LOCAL_RANK"))
+    device = std::atoi(e2);
+  for (int i = 0; i < argc_dlaf; ++i) {
+    const std::string arg = argv_dlaf[i] ? argv_dlaf[i] : "";
+    if (arg.rfind("--dlaf:device=", 0) == 0)
+      device = std::atoi(arg.c_str() + 14);
+    else if (arg == "--dlaf:print-config")
+      print_config = true;
+  }
+  int ndev = 0;
+  const cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    std::fprintf(stderr, "[dlaf_b200] no CUDA device available (%s): this library has no CPU path\n",
+                 cudaGetErrorString(e));
+    std::fflush(stderr);
+    std::abort();
+  }
+  if (device < 0)
+    device = 0;
+  device %= ndev;
+  DLAF_CUDA_CHECK(cudaSetDevice(device));
+  g_device = device;
+  if (print_config) {
+    cudaDeviceProp p;
+    DLAF_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    std::printf("dlaf_b200 configuration:\n  device = %d (%s, sm_%d%d, %d SMs)\n  granularity = 128 (real) / 64 (complex)\n",
+                device, p.name, p.major, p.minor, p.multiProcessorCount);
+  }
+  g_initialized = true;
+}
+
+void dlaf_finalize(void) noexcept {
+  if (!g_initialized)
+    return;
+  g_grids.clear();
+  g_initialized = false;
+}
+
+void dlaf_b200_get_unique_id(void* id128) noexcept {
+  ncclUniqueId id;
+  DLAF_NCCL_CHECK(ncclGetUniqueId(&id));
+  static_assert(sizeof(id) == DLAF_B200_UNIQUE_ID_BYTES, "unique id size");
+  std::memcpy(id128, &id, sizeof(id));
+}
+
+struct dlaf_b200_comm* dlaf_b200_comm_create(const void* id128, int rank, int nranks) noexcept {
+  ensure_initialized();
+  return comm_create(id128, rank, nranks);
+}
+
+void dlaf_b200_comm_destroy(struct dlaf_b200_comm* comm) noexcept {
+  comm_destroy(comm);
+}
+
+int dlaf_create_grid(DLAF_Comm comm, int nprow, int npcol, char order) noexcept {
+  ensure_initialized();
+  std::unique_ptr<GridCtx> c(new GridCtx);
+  c->grid.reset(new CommGrid(comm, nprow, npcol, order));
+  DLAF_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  const int ctx = g_next_ctx--;
+  g_grids[ctx] = std::move(c);
+  return ctx;
+}
+
+void dlaf_free_grid(int context) noexcept {
+  g_grids.erase(context);
+}
+
+void dlaf_free_all_grids(void) noexcept {
+  g_grids.clear();
+}
+
+char grid_ordering(DLAF_Comm comm, int nprow, int npcol, int myprow, int mypcol) noexcept {
+  const Comm* c = comm;
+  const int rank = c ? c->rank : 0;
+  const bool row_major = (rank == myprow * npcol + mypcol);
+  const bool col_major = (rank == mypcol * nprow + myprow);
+  (void) col_major;
+  return row_major ? 'R' : 'C';
+}
+
+struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int i, const int j,
+                                            const int desc[9]) noexcept {
+  DLAF_B200_ASSERT(i == 1 && j == 1, "only the full matrix (i == j == 1) is supported");
+  struct DLAF_descriptor d = {m, n, desc[4], desc[5], desc[6], desc[7], i - 1, j - 1, desc[8]};
+  return d;
+}
+
+#define DLAF_B200_DEFINE(sfx, T)                                                                              \
+  int dlaf_cholesky_factorization_##sfx(const int ctx, const char uplo, T* a,                                 \
+                                        const struct DLAF_descriptor d) noexcept {                            \
+    return cholesky_host<T>(ctx, uplo, a, d);                                                                 \
+  }                                                                                                           \
+  void dlaf_p##sfx##potrf(const char uplo, const int n, T* a, const int ia, const int ja, const int desca[9], \
+                          int* info) noexcept {                                                               \
+    pxpotrf<T>(uplo, n, a, ia, ja, desca, info);                                                              \
+  }                                                                                                           \
+  int dlaf_b200_cholesky_factorization_device_##sfx(int ctx, char uplo, T* a_dev, struct DLAF_descriptor d,   \
+                                                    void* stream) noexcept {                                  \
+    return cholesky_device<T>(ctx, uplo, a_dev, d, stream);                                                   \
+  }                                                                                                           \
+  void dlaf_b200_set_random_hermitian_positive_definite_##sfx(int ctx, T* a,                                  \
+                                                              struct DLAF_descriptor d) noexcept {            \
+    random_hpd<T>(ctx, a, d);                                                                                 \
+  }
+
+DLAF_B200_DEFINE(d, double)
+#ifdef DLAF_B200_ALL_TYPES
+DLAF_B200_DEFINE(s, float)
+DLAF_B200_DEFINE(c, dlaf_complex_c)
+DLAF_B200_DEFINE(z, dlaf_complex_z)
+#endif
+
+int dlaf_b200_wait(int ctx, void* stream) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  if (c.last_type < 0 || !c.slot[c.last_type])
+    return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int info = c.slot[c.last_type]->info(s);
+  return reduce_info(c, info, s);
+}
+
+long dlaf_b200_last_launch_count(int ctx) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  if (c.last_type < 0 || !c.slot[c.last_type])
+    return 0;
+  return c.slot[c.last_type]->launches();
+}
+
+void dlaf_b200_grid_info(int ctx, int out[4]) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  out[0] = c.grid->P;
+  out[1] = c.grid->Q;
+  out[2] = c.grid->row;
+  out[3] = c.grid->col;
+}
+
+int dlaf_b200_local_rows(int ctx, struct DLAF_descriptor d) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  return static_cast<int>(user_geometry(*c.grid, d).lrows);
+}
+
+int dlaf_b200_local_cols(int ctx, struct DLAF_descriptor d) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  return static_cast<int>(user_geometry(*c.grid, d).lcols);
+}
+
+}  // extern "C"

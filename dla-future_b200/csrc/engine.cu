@@ -1,0 +1,447 @@
+// See engine.h.
+#include "engine.h"
+
+#include <cstdint>
+
+#include "comm.h"
+#include "common.h"
+
+namespace dlaf_b200 {
+
+namespace {
+inline int cnt_tiles(long g_end, int r, int grid) {
+  // number of global tile indices g in [0, g_end) with g % grid == r
+  return g_end > r ? static_cast<int>((g_end - r + grid - 1) / grid) : 0;
+}
+}  // namespace
+
+template <class T>
+PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclComm_t col_comm)
+    : geo_(g), row_comm_(row_comm), col_comm_(col_comm) {
+  DLAF_B200_ASSERT(g.n >= 0 && g.nb >= 1, "matrix / block size");
+  DLAF_B200_ASSERT(g.P >= 1 && g.Q >= 1 && g.prow >= 0 && g.prow < g.P && g.pcol >= 0 && g.pcol < g.Q,
+                   "grid coordinates");
+  DLAF_B200_ASSERT(g.P == 1 || col_comm != nullptr, "column communicator required when P > 1");
+  DLAF_B200_ASSERT(g.Q == 1 || row_comm != nullptr, "row communicator required when Q > 1");
+  nbp_ = static_cast<int>(round_up(g.nb, G));
+  nt_ = ceil_div(g.n, g.nb);
+  ns_ = nbp_ / G;
+  ltr_ = cnt_tiles(nt_, g.prow, g.P);
+  ltc_ = cnt_tiles(nt_, g.pcol, g.Q);
+  own_ld_ = static_cast<long>(ltr_) * nbp_;
+  ld_ = own_ld_;
+
+  int least, greatest;
+  DLAF_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sH_, cudaStreamNonBlocking, greatest));
+  DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sL_, cudaStreamNonBlocking, least));
+  DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start_, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evP_[i], cudaEventDisableTiming));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evB_[i], cudaEventDisableTiming));
+  }
+  const size_t wsz = static_cast<size_t>(ns_) * G * G;
+  const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
+  for (int i = 0; i < 2; ++i) {
+    if (geo_.P > 1) {
+      DLAF_CUDA_CHECK(cudaMalloc(&diagbuf_[i], sizeof(T) * (tsz + wsz)));
+      DLAF_CUDA_CHECK(cudaMalloc(&panelT_[i], sizeof(T) * tsz * (ltc_ > 0 ? ltc_ : 1)));
+    }
+    else {
+      DLAF_CUDA_CHECK(cudaMalloc(&wbuf_[i], sizeof(T) * wsz));
+    }
+    if (geo_.P * geo_.Q > 1)
+      DLAF_CUDA_CHECK(cudaMalloc(&panel_[i], sizeof(T) * tsz * (ltr_ > 0 ? ltr_ : 1)));
+  }
+  DLAF_CUDA_CHECK(cudaMalloc(&d_info_, sizeof(int)));
+  DLAF_CUDA_CHECK(cudaMallocHost(&h_info_, sizeof(int)));
+  *h_info_ = 0;
+}
+
+template <class T>
+PotrfEngine<T>::~PotrfEngine() {
+  cudaStreamSynchronize(sH_);
+  cudaStreamSynchronize(sL_);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(wbuf_[i]);
+    cudaFree(diagbuf_[i]);
+    cudaFree(panel_[i]);
+    cudaFree(panelT_[i]);
+    cudaEventDestroy(evP_[i]);
+    cudaEventDestroy(evB_[i]);
+  }
+  cudaEventDestroy(ev_start_);
+  cudaFree(own_slab_);
+  cudaFree(d_info_);
+  cudaFreeHost(h_info_);
+  cudaStreamDestroy(sH_);
+  cudaStreamDestroy(sL_);
+}
+
+template <class T>
+int PotrfEngine<T>::cnt_rows(long g_end) const {
+  return cnt_tiles(g_end, geo_.prow, geo_.P);
+}
+template <class T>
+int PotrfEngine<T>::cnt_cols(long g_end) const {
+  return cnt_tiles(g_end, geo_.pcol, geo_.Q);
+}
+
+template <class T>
+LayoutParams PotrfEngine<T>::layout(long ldu, bool transposed) const {
+  LayoutParams p;
+  p.n = geo_.n;
+  p.nb = geo_.nb;
+  p.nbp = nbp_;
+  p.nt = nt_;
+  p.P = geo_.P;
+  p.Q = geo_.Q;
+  p.prow = geo_.prow;
+  p.pcol = geo_.pcol;
+  p.ltr = ltr_;
+  p.ltc = ltc_;
+  p.ld = ld_;
+  p.ldu = ldu;
+  p.transposed = transposed ? 1 : 0;
+  return p;
+}
+
+template <class T>
+T* PotrfEngine<T>::slab() {
+  if (own_slab_ == nullptr && ltr_ > 0 && ltc_ > 0) {
+    const size_t bytes = sizeof(T) * static_cast<size_t>(own_ld_) * ltc_ * nbp_;
+    DLAF_CUDA_CHECK(cudaMalloc(&own_slab_, bytes));
+  }
+  if (!external_) {
+    data_ = own_slab_;
+    ld_ = own_ld_;
+  }
+  return own_slab_;
+}
+
+template <class T>
+bool PotrfEngine<T>::can_run_in_place(const EngineGeometry& g, const void* dev, long ld) {
+  return g.nb % G == 0 && g.n % g.nb == 0 && ld % 2 == 0 && (reinterpret_cast<uintptr_t>(dev) & 15) == 0;
+}
+
+template <class T>
+void PotrfEngine<T>::bind_external(T* dev, long ld) {
+  DLAF_B200_ASSERT(can_run_in_place(geo_, dev, ld), "in-place operation needs unpadded, aligned tiles");
+  external_ = true;
+  data_ = dev;
+  ld_ = ld;
+}
+
+template <class T>
+void PotrfEngine<T>::unbind_external() {
+  external_ = false;
+  data_ = own_slab_;
+  ld_ = own_ld_;
+}
+
+template <class T>
+void PotrfEngine<T>::load(const T* user, long ldu, bool transposed, cudaStream_t s) {
+  DLAF_B200_ASSERT(!external_, "load() targets the engine's own slab");
+  if (ltr_ == 0 || ltc_ == 0)
+    return;
+  slab();
+  const LayoutParams p = layout(ldu, transposed);
+  if (padded())
+    launch_pad_identity<T>(data_, p, s);
+  launch_to_slab<T>(data_, user, p, s);
+}
+
+template <class T>
+void PotrfEngine<T>::store(T* user, long ldu, bool transposed, cudaStream_t s) {
+  DLAF_B200_ASSERT(!external_, "store() reads the engine's own slab");
+  if (ltr_ == 0 || ltc_ == 0)
+    return;
+  launch_from_slab<T>(data_, user, layout(ldu, transposed), s);
+}
+
+template <class T>
+void PotrfEngine<T>::gemm(const GemmArgsT<T>& a, cudaStream_t st) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0)
+    return;
+  launch_gemm_nt<T>(a, st);
+  ++launches_;
+}
+
+// Diagonal tile (nbp x nbp) = ns diagonal blocks of G: block Cholesky + inverse (potrf_tile.cu), the
+// blocks below via GEMM with the inverse, the rest of the tile via a masked SYRK-shaped GEMM.
+template <class T>
+void PotrfEngine<T>::factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_t st) {
+  for (int j = 0; j < ns_; ++j) {
+    T* tjj = tile + static_cast<long>(j) * G * (1 + ld);
+    T* wj = w + static_cast<long>(j) * G * G;
+    launch_potrf_inv<T>(tjj, ld, wj, G, d_info_, k * geo_.nb + j * G, st);
+    ++launches_;
+    const int m = (ns_ - 1 - j) * G;
+    if (m == 0)
+      break;
+    T* below = tjj + G;
+    GemmArgsT<T> a{};
+    a.A = below;
+    a.lda = ld;
+    a.B = wj;
+    a.ldb = G;
+    a.C = below;  // in place: below <- below * inv(L_jj)^H
+    a.ldc = ld;
+    a.M = m;
+    a.N = G;
+    a.K = G;
+    a.alpha = 1.0;
+    a.beta = 0.0;
+    a.mask = kMaskNone;
+    a.nbp = nbp_;
+    a.P = a.Q = 1;
+    gemm(a, st);
+    GemmArgsT<T> u{};
+    u.A = below;
+    u.lda = ld;
+    u.B = below;
+    u.ldb = ld;
+    u.C = tjj + static_cast<long>(G) * (1 + ld);
+    u.ldc = ld;
+    u.M = m;
+    u.N = m;
+    u.K = G;
+    u.alpha = -1.0;
+    u.beta = 1.0;
+    u.mask = kMaskLower;  // relative to the diagonal of this sub-block
+    u.nbp = 1 << 30;
+    u.P = u.Q = 1;
+    gemm(u, st);
+  }
+}
+
+// Panel TRSM  B <- B * L_kk^-H  (reference: trsm(Right, Lower, ConjTrans, NonUnit), impl.h:62-66) as
+// block substitution over the ns diagonal blocks: every step is a tensor-core GEMM.
+template <class T>
+void PotrfEngine<T>::trsm_panel(T* b, long ldb, int m, const T* tkk, long ldt, const T* w, cudaStream_t st) {
+  for (int j = 0; j < ns_; ++j) {
+    T* bj = b + static_cast<long>(j) * G * ldb;
+    if (j > 0) {
+      GemmArgsT<T> a{};
+      a.A = b;
+      a.lda = ldb;
+      a.B = tkk + static_cast<long>(j) * G;  // row block j of L_kk, columns [0, j*G)
+      a.ldb = ldt;
+      a.C = bj;
+      a.ldc = ldb;
+      a.M = m;
+      a.N = G;
+      a.K = j * G;
+      a.alpha = -1.0;
+      a.beta = 1.0;
+      a.mask = kMaskNone;
+      a.nbp = nbp_;
+      a.P = a.Q = 1;
+      gemm(a, st);
+    }
+    GemmArgsT<T> s{};
+    s.A = bj;
+    s.lda = ldb;
+    s.B = w + static_cast<long>(j) * G * G;
+    s.ldb = G;
+    s.C = bj;  // in place
+    s.ldc = ldb;
+    s.M = m;
+    s.N = G;
+    s.K = G;
+    s.alpha = 1.0;
+    s.beta = 0.0;
+    s.mask = kMaskNone;
+    s.nbp = nbp_;
+    s.P = s.Q = 1;
+    gemm(s, st);
+  }
+}
+
+// P_k on stream H: diagonal tile, its broadcast down the owning process column, the panel TRSM, and
+// the two panel broadcasts (row-wise, then "transposed" column-wise: broadcast_panel.h:107-188).
+template <class T>
+void PotrfEngine<T>::panel_step(int k) {
+  using NT = NcclType<T>;
+  const int P = geo_.P, Q = geo_.Q;
+  const int owner_r = k % P, owner_c = k % Q;
+  const bool in_row = (geo_.prow == owner_r), in_col = (geo_.pcol == owner_c);
+  const int lkr = k / P, lkc = k / Q;
+  const int li1 = cnt_rows(k + 1), lj1 = cnt_cols(k + 1);
+  const int mt = ltr_ - li1;
+  const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
+  const size_t wsz = static_cast<size_t>(ns_) * G * G;
+  const int slot = k % 2;
+
+  if (in_col) {
+    const T* tkk = nullptr;
+    long ldt = 0;
+    const T* w = nullptr;
+    if (P > 1) {
+      T* dbuf = diagbuf_[slot];
+      if (in_row) {
+        T* tile = tile_ptr(lkr, lkc);
+        factor_diag_tile(tile, ld_, dbuf + tsz, k, sH_);
+        DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dbuf, sizeof(T) * nbp_, tile, sizeof(T) * ld_, sizeof(T) * nbp_,
+                                          nbp_, cudaMemcpyDeviceToDevice, sH_));
+      }
+      DLAF_NCCL_CHECK(ncclBroadcast(dbuf, dbuf, (tsz + wsz) * NT::mult, NT::value, col_comm_rank(owner_r),
+                                    col_comm_, sH_));
+      tkk = dbuf;
+      ldt = nbp_;
+      w = dbuf + tsz;
+    }
+    else {
+      T* tile = tile_ptr(lkr, lkc);
+      factor_diag_tile(tile, ld_, wbuf_[slot], k, sH_);
+      tkk = tile;
+      ldt = ld_;
+      w = wbuf_[slot];
+    }
+    if (mt > 0)
+      trsm_panel(tile_ptr(li1, lkc), ld_, mt * nbp_, tkk, ldt, w, sH_);
+  }
+
+  if (k < nt_ - 1 && P * Q > 1) {
+    if (mt > 0) {
+      if (in_col) {
+        launch_pack_panel<T>(tile_ptr(li1, lkc), ld_, panel_[slot], nbp_, mt, sH_);
+        ++launches_;
+      }
+      if (Q > 1)
+        DLAF_NCCL_CHECK(ncclBroadcast(panel_[slot], panel_[slot], tsz * mt * NT::mult, NT::value,
+                                      row_comm_rank(owner_c), row_comm_, sH_));
+    }
+    if (P > 1 && ltc_ - lj1 > 0) {
+      DLAF_NCCL_CHECK(ncclGroupStart());
+      for (int lj = lj1; lj < ltc_; ++lj) {
+        const long gj = static_cast<long>(lj) * Q + geo_.pcol;
+        const int root_v = static_cast<int>(gj % P);
+        T* recv = panelT_[slot] + tsz * (lj - lj1);
+        const T* send = recv;
+        if (root_v == geo_.prow)
+          send = panel_[slot] + tsz * (gj / P - li1);
+        DLAF_NCCL_CHECK(ncclBroadcast(send, recv, tsz * NT::mult, NT::value, col_comm_rank(root_v),
+                                      col_comm_, sH_));
+      }
+      DLAF_NCCL_CHECK(ncclGroupEnd());
+    }
+  }
+  DLAF_CUDA_CHECK(cudaEventRecord(evP_[slot], sH_));
+}
+
+// U_k: trailing update of my local tiles with panel k. lookahead = only block column k+1 (if mine),
+// otherwise everything to the right of it.
+template <class T>
+void PotrfEngine<T>::update(int k, bool lookahead, cudaStream_t st) {
+  const int P = geo_.P, Q = geo_.Q;
+  const int li1 = cnt_rows(k + 1), lj1 = cnt_cols(k + 1);
+  if (ltr_ - li1 <= 0 || ltc_ - lj1 <= 0)
+    return;
+  const bool own_next = ((k + 1) % Q == geo_.pcol);
+  int cj0, ncols;
+  if (lookahead) {
+    if (!own_next)
+      return;
+    cj0 = lj1;
+    ncols = 1;
+  }
+  else {
+    cj0 = own_next ? lj1 + 1 : lj1;
+    ncols = ltc_ - cj0;
+  }
+  if (ncols <= 0)
+    return;
+  const long gj0 = static_cast<long>(cj0) * Q + geo_.pcol;
+  const int ri0 = cnt_rows(gj0);  // first local row tile on or below the diagonal of column cj0
+  const int mrows = (ltr_ - ri0) * nbp_;
+  if (mrows <= 0)
+    return;
+  const int slot = k % 2;
+  const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
+  const int lkc = k / Q;
+
+  GemmArgsT<T> a{};
+  a.C = tile_ptr(ri0, cj0);
+  a.ldc = ld_;
+  a.M = mrows;
+  a.N = ncols * nbp_;
+  a.K = nbp_;
+  a.alpha = -1.0;
+  a.beta = 1.0;
+  a.mask = kMaskLower;
+  a.nbp = nbp_;
+  a.P = P;
+  a.Q = Q;
+  a.prow = geo_.prow;
+  a.pcol = geo_.pcol;
+  a.ti0 = ri0;
+  a.tj0 = cj0;
+  if (P * Q == 1) {
+    // panel and transposed panel are the block column k of the matrix itself (no copy, like the
+    // reference's setTile aliasing, impl.h:261)
+    a.A = tile_ptr(ri0, lkc);
+    a.lda = ld_;
+    a.B = tile_ptr(cj0, lkc);
+    a.ldb = ld_;
+  }
+  else {
+    a.A = panel_[slot] + tsz * (ri0 - li1);
+    a.lda = nbp_;
+    a.a_ts = static_cast<long>(tsz);
+    if (P == 1) {
+      // every row is local: tile (gj, k) sits in my panel at index gj - (k+1)
+      a.B = panel_[slot] + tsz * (gj0 - (k + 1));
+      a.b_ts = static_cast<long>(tsz) * Q;
+    }
+    else {
+      a.B = panelT_[slot] + tsz * (cj0 - lj1);
+      a.b_ts = static_cast<long>(tsz);
+    }
+    a.ldb = nbp_;
+  }
+  gemm(a, st);
+}
+
+template <class T>
+void PotrfEngine<T>::factorize(cudaStream_t s) {
+  launches_ = 0;
+  if (nt_ == 0)
+    return;
+  if (!external_)
+    slab();
+  DLAF_CUDA_CHECK(cudaEventRecord(ev_start_, s));
+  DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, ev_start_, 0));
+  DLAF_CUDA_CHECK(cudaStreamWaitEvent(sL_, ev_start_, 0));
+  DLAF_CUDA_CHECK(cudaMemsetAsync(d_info_, 0, sizeof(int), sH_));
+
+  panel_step(0);
+  for (int k = 0; k < nt_ - 1; ++k) {
+    // bulk of U_k on the low-priority stream
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sL_, evP_[k % 2], 0));
+    update(k, false, sL_);
+    DLAF_CUDA_CHECK(cudaEventRecord(evB_[k % 2], sL_));
+    // critical path on the high-priority stream: U_k(k+1), then P_{k+1}
+    if (k >= 1)
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evB_[(k - 1) % 2], 0));
+    update(k, true, sH_);
+    panel_step(k + 1);
+  }
+  DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evP_[(nt_ - 1) % 2], 0));
+  if (nt_ >= 2)
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evB_[(nt_ - 2) % 2], 0));
+  DLAF_CUDA_CHECK(cudaMemcpyAsync(h_info_, d_info_, sizeof(int), cudaMemcpyDeviceToHost, s));
+}
+
+template <class T>
+int PotrfEngine<T>::info(cudaStream_t s) {
+  DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+  int v = *h_info_;
+  if (v > geo_.n)
+    v = 0;  // cannot happen (identity padding never fails); keep the LAPACK range
+  return v;
+}
+
+template class PotrfEngine<double>;
+
+}  // namespace dlaf_b200

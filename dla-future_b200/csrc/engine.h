@@ -1,0 +1,112 @@
+// Host scheduler of the B200 POTRF path: issues the hand-written kernels of one rank (= one GPU) in
+// look-ahead order over two CUDA streams + events and, on a P x Q grid, the NCCL panel broadcasts.
+//
+// It replaces Cholesky<Backend::GPU, Device::GPU, T>::call_L (local and distributed,
+// include/dlaf/factorization/cholesky/impl.h:150-313) together with the machinery underneath it:
+// the pika sender DAG (sender/transform.h:52-110), the per-tile async RW mutexes
+// (matrix/internal/tile_pipeline.h:19-81), the round-robin panel workspaces (impl.h:218-221) and the
+// per-tile MPI_Ibcast pipeline (communication/broadcast_panel.h:107-188). call_U is served by the same
+// code on the conjugate-transposed problem (see layout.cuh).
+//
+// Dependencies per step k (P_k = diagonal tile + panel of column k, U_k(j) = update of block column j
+// with panel k):   P_k <- U_{k-1}(k);   U_k(j) <- P_k, U_{k-1}(j).
+// Stream H (high priority):  U_{k-1}(k), P_k, broadcasts of panel k      — the critical path
+// Stream L (low priority):   U_k(k+2 ..)                                 — the bulk, ~95 % of the flops
+// which is exactly the reference's 1-column look-ahead priority rule (impl.h:171-173, :280-281).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include "gemm_args.h"
+#include "layout.cuh"
+#include "potrf_tile.cuh"
+#include "types.h"
+
+namespace dlaf_b200 {
+
+struct EngineGeometry {
+  long n = 0;  // global matrix size
+  int nb = 1;  // user tile (= distribution block) size
+  // ENGINE process grid and my source-rank-adjusted ("virtual") coordinates in it. For uplo == 'U'
+  // the caller passes the transposed grid.
+  int P = 1, Q = 1, prow = 0, pcol = 0;
+  // NCCL rank (inside row_comm / col_comm) of virtual coordinate 0, i.e. the source rank offsets.
+  int src_in_col_comm = 0;  // rank in col_comm (size P) of virtual row 0
+  int src_in_row_comm = 0;  // rank in row_comm (size Q) of virtual column 0
+};
+
+template <class T>
+class PotrfEngine {
+public:
+  static constexpr int G = Gran<T>::value;
+
+  PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclComm_t col_comm);
+  ~PotrfEngine();
+  PotrfEngine(const PotrfEngine&) = delete;
+  PotrfEngine& operator=(const PotrfEngine&) = delete;
+
+  // --- geometry
+  long n() const { return geo_.n; }
+  int nb() const { return geo_.nb; }
+  int nbp() const { return nbp_; }
+  int nt() const { return nt_; }
+  int local_tile_rows() const { return ltr_; }
+  int local_tile_cols() const { return ltc_; }
+  bool padded() const { return nbp_ != geo_.nb || geo_.n % geo_.nb != 0; }
+  LayoutParams layout(long ldu, bool transposed) const;
+
+  // --- storage: either the engine's own padded slab, or (no padding, 16-byte aligned, even ld) the
+  // caller's device memory used in place.
+  T* slab();
+  long slab_ld() const { return ld_; }
+  void bind_external(T* dev, long ld);
+  void unbind_external();
+  static bool can_run_in_place(const EngineGeometry& g, const void* dev, long ld);
+
+  // --- boundary copies (device pointers in the reference's local layout)
+  void load(const T* user, long ldu, bool transposed, cudaStream_t s);
+  void store(T* user, long ldu, bool transposed, cudaStream_t s);
+
+  // --- the factorization: asynchronous w.r.t. the host; ordered after everything already enqueued on
+  // `s` and complete (for stream order purposes) when `s` reaches the point after this call.
+  void factorize(cudaStream_t s);
+  // LAPACK-style info of the last factorize (0 = success, k = leading minor of order k not positive
+  // definite). Synchronises `s`.
+  int info(cudaStream_t s);
+
+  long launches() const { return launches_; }  // kernels launched by the last factorize()
+
+private:
+  void panel_step(int k);
+  void update(int k, bool lookahead, cudaStream_t st);
+  void factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_t st);
+  void trsm_panel(T* b, long ldb, int m, const T* tkk, long ldt, const T* w, cudaStream_t st);
+  void gemm(const GemmArgsT<T>& a, cudaStream_t st);
+  int cnt_rows(long g_end) const;  // local row tiles with global index < g_end
+  int cnt_cols(long g_end) const;
+  int col_comm_rank(int vrow) const { return (vrow + geo_.src_in_col_comm) % geo_.P; }
+  int row_comm_rank(int vcol) const { return (vcol + geo_.src_in_row_comm) % geo_.Q; }
+  T* tile_ptr(int li, int lj) { return data_ + static_cast<long>(li) * nbp_ + static_cast<long>(lj) * nbp_ * ld_; }
+
+  EngineGeometry geo_;
+  ncclComm_t row_comm_, col_comm_;
+  int nbp_, nt_, ltr_, ltc_, ns_;
+  long ld_ = 0;
+  T* data_ = nullptr;      // active storage (own slab or external)
+  T* own_slab_ = nullptr;
+  long own_ld_ = 0;
+  bool external_ = false;
+
+  cudaStream_t sH_ = nullptr, sL_ = nullptr;
+  cudaEvent_t ev_start_ = nullptr, evP_[2] = {nullptr, nullptr}, evB_[2] = {nullptr, nullptr};
+  T* wbuf_[2] = {nullptr, nullptr};     // inverses of the diagonal blocks (1 x 1 column grid)
+  T* diagbuf_[2] = {nullptr, nullptr};  // diagonal tile + inverses, broadcast down the process column
+  T* panel_[2] = {nullptr, nullptr};    // column panel, tile-contiguous
+  T* panelT_[2] = {nullptr, nullptr};   // transposed panel (tiles (j,k) for my local columns j)
+  int* d_info_ = nullptr;
+  int* h_info_ = nullptr;
+  long launches_ = 0;
+};
+
+}  // namespace dlaf_b200

@@ -1,0 +1,228 @@
+// fp64 tensor-core (DMMA.8x8x4) NT GEMM used by every dense contraction of the POTRF path:
+//
+//   C(MxN) = beta * C + alpha * A(MxK) * B(NxK)^T        all column-major
+//
+// It replaces the reference's three BLAS tile calls (include/dlaf/factorization/cholesky/impl.h):
+//   * gemmTrailingMatrixTile  (impl.h:82-94,  blas/tile.h:249-261)  A_ij -= A_ik A_jk^H
+//   * herkTrailingDiagTile    (impl.h:69-80,  blas/tile.h:293-304)  A_jj -= A_jk A_jk^H (lower only)
+//   * trsmPanelTile           (impl.h:55-67,  blas/tile.h:337-349)  A_ik <- A_ik L_kk^-H, as block
+//     substitution with pre-inverted 128x128 diagonal blocks (potrf_tile.cu) -> pure GEMMs.
+// One launch covers the WHOLE local trailing matrix of a step (not one launch per tile): the
+// lower-triangular structure is a tile-level mask evaluated on global (block-cyclic) indices.
+//
+// sm_100a notes: tcgen05 has no f64 kind, so the fp64 tensor path is the warp-level
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4; all wider f64 shapes lower to it on sm_100a).
+// Operands are staged global->shared with 16-byte cp.async (LDGSTS) in a 4-stage ring.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "gemm_args.h"
+
+namespace dlaf_b200 {
+
+using GemmArgs = GemmArgsT<double>;
+
+namespace gemm_detail {
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;\n" ::);
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+}  // namespace gemm_detail
+
+template <int BM_, int BN_, int BK_, int STAGES_>
+struct GemmCfg {
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, STAGES = STAGES_;
+  static constexpr int THREADS = 256;
+  // +4 doubles of padding: the DMMA fragment read (k = lane&3, m = lane>>2) then hits 16 distinct
+  // 8-byte banks per half-warp (row stride == 4 mod 16 doubles) -> conflict-free LDS.64.
+  static constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
+  static constexpr int A_STAGE = BK * LDA_S, B_STAGE = BK * LDB_S;
+  static constexpr int LDC_S = BM + 2;  // epilogue staging tile (reuses the operand ring)
+  static constexpr int RING_BYTES = STAGES * (A_STAGE + B_STAGE) * 8;
+  static constexpr int SMEM_BYTES = RING_BYTES > BN * LDC_S * 8 ? RING_BYTES : BN * LDC_S * 8;
+  static constexpr int WARPS_M = 2, WARPS_N = 4;
+  static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
+  static constexpr int FM = WM / 8, FN = WN / 8;              // 8x8 fragments per warp
+};
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_f64_kernel(const GemmArgs p) {
+  using namespace gemm_detail;
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  constexpr int FM = Cfg::FM, FN = Cfg::FN;
+
+  extern __shared__ __align__(16) double smem[];
+  double* As = smem;
+  double* Bs = smem + STAGES * Cfg::A_STAGE;
+
+  const int row0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  long grow0, gcol0;
+  const int cls = classify_tile(p, row0, col0, BM, BN, grow0, gcol0);
+  if (cls == 0)
+    return;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM;
+  const int wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
+
+  const double* Ag = p.A + (p.a_ts ? (row0 / p.nbp) * p.a_ts + row0 % p.nbp : row0);
+  const double* Bg = p.B + (p.b_ts ? (col0 / p.nbp) * p.b_ts + col0 % p.nbp : col0);
+  const int KT = p.K / BK;
+
+  if (p.beta != 0.0) {
+    // Pull the C tile towards L2 now; the epilogue reads it ~K/16 stages later.
+    const double* Cg0 = p.C + row0 + static_cast<long>(col0) * p.ldc;
+#pragma unroll
+    for (int i = 0; i < (BM / 16) * BN / Cfg::THREADS; ++i) {
+      const int l = tid + i * Cfg::THREADS;
+      const int col = l / (BM / 16), seg = l % (BM / 16);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg0 + seg * 16 + static_cast<long>(col) * p.ldc));
+    }
+  }
+
+  auto load_stage = [&](int slot, int kt) {
+    const int k0 = kt * BK;
+    double* as = As + slot * Cfg::A_STAGE;
+    double* bs = Bs + slot * Cfg::B_STAGE;
+#pragma unroll
+    for (int i = 0; i < (BK * BM / 2) / Cfg::THREADS; ++i) {
+      const int c = tid + i * Cfg::THREADS;
+      const int k = c / (BM / 2), m2 = c % (BM / 2);
+      cp_async16(as + k * Cfg::LDA_S + 2 * m2, Ag + static_cast<long>(k0 + k) * p.lda + 2 * m2);
+    }
+#pragma unroll
+    for (int i = 0; i < (BK * BN / 2) / Cfg::THREADS; ++i) {
+      const int c = tid + i * Cfg::THREADS;
+      const int k = c / (BN / 2), n2 = c % (BN / 2);
+      cp_async16(bs + k * Cfg::LDB_S + 2 * n2, Bg + static_cast<long>(k0 + k) * p.ldb + 2 * n2);
+    }
+  };
+
+  double acc[FM][FN][2];
+#pragma unroll
+  for (int i = 0; i < FM; ++i)
+#pragma unroll
+    for (int j = 0; j < FN; ++j)
+      acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < KT)
+      load_stage(s, s);
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < KT; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nk = kt + STAGES - 1;
+      if (nk < KT)
+        load_stage(nk % STAGES, nk);
+      cp_async_commit();
+    }
+    const double* as = As + (kt % STAGES) * Cfg::A_STAGE + wm0 + g;
+    const double* bs = Bs + (kt % STAGES) * Cfg::B_STAGE + wn0 + g;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      double af[FM], bf[FN];
+#pragma unroll
+      for (int i = 0; i < FM; ++i)
+        af[i] = as[(kk * 4 + tig) * Cfg::LDA_S + 8 * i];
+#pragma unroll
+      for (int j = 0; j < FN; ++j)
+        bf[j] = bs[(kk * 4 + tig) * Cfg::LDB_S + 8 * j];
+#pragma unroll
+      for (int i = 0; i < FM; ++i)
+#pragma unroll
+        for (int j = 0; j < FN; ++j)
+          dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+  // In-place use (C aliases A, N == BN): every read of this CTA's A rows has landed above, and no
+  // other CTA touches these rows, so the epilogue may overwrite them.
+  __syncthreads();
+
+  // Epilogue: stage the accumulator tile through the (now idle) operand ring so that C is read and
+  // written with 16-byte accesses, 1 KB contiguous per column (coalesced), all loads of a batch in
+  // flight before the first store. Cs is column-major with LDC_S == 2 (mod 8): the fragment store
+  // (row = g, col = 2*tig+e) then covers 16 distinct 8-byte banks per half-warp.
+  constexpr int LDC_S = Cfg::LDC_S;
+  double* Cs = smem;
+#pragma unroll
+  for (int i = 0; i < FM; ++i)
+#pragma unroll
+    for (int j = 0; j < FN; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        Cs[(wn0 + 8 * j + 2 * tig + e) * LDC_S + wm0 + 8 * i + g] = acc[i][j][e];
+  __syncthreads();
+
+  const bool use_beta = (p.beta != 0.0);
+  constexpr int CHUNKS = BM * BN / 2 / Cfg::THREADS;  // 16-byte chunks per thread
+  constexpr int BATCH = 8;
+  double* Cg = p.C + row0 + static_cast<long>(col0) * p.ldc;
+#pragma unroll 1
+  for (int b0 = 0; b0 < CHUNKS; b0 += BATCH) {
+    double2 cv[BATCH];
+    if (use_beta) {
+#pragma unroll
+      for (int b = 0; b < BATCH; ++b) {
+        const int q = tid + (b0 + b) * Cfg::THREADS;
+        const int col = q / (BM / 2), m2 = q % (BM / 2);
+        cv[b] = *reinterpret_cast<const double2*>(Cg + 2 * m2 + static_cast<long>(col) * p.ldc);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < BATCH; ++b) {
+      const int q = tid + (b0 + b) * Cfg::THREADS;
+      const int col = q / (BM / 2), m2 = q % (BM / 2);
+      const double2 a = *reinterpret_cast<const double2*>(Cs + col * LDC_S + 2 * m2);
+      double2 v;
+      v.x = p.alpha * a.x;
+      v.y = p.alpha * a.y;
+      if (use_beta) {
+        v.x += p.beta * cv[b].x;
+        v.y += p.beta * cv[b].y;
+      }
+      double* dst = Cg + 2 * m2 + static_cast<long>(col) * p.ldc;
+      if (cls == 1) {
+        *reinterpret_cast<double2*>(dst) = v;
+      }
+      else {  // tile straddles the diagonal: element mask, never touch the other triangle
+        const long gr = grow0 + 2 * m2, gc = gcol0 + col;
+        if (gr >= gc)
+          dst[0] = v.x;
+        if (gr + 1 >= gc)
+          dst[1] = v.y;
+      }
+    }
+  }
+}
+
+using GemmCfg128 = GemmCfg<128, 128, 16, 4>;
+
+// Host launcher (defined in gemm_dmma.cu).
+void launch_gemm_nt_f64(const GemmArgs& args, cudaStream_t stream);
+
+}  // namespace dlaf_b200

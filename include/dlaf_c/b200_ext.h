@@ -1,0 +1,36 @@
+/* dlaf_c/b200_ext.h — entry points that have no C counterpart in the reference but correspond to its
+ * C++ surface, exposed over the same C ABI so that host languages bind them the same way:
+ *
+ *  * device-resident factorization = dlaf::cholesky_factorization<Backend::GPU, Device::GPU, T>
+ *    (include/dlaf/factorization/cholesky.h:41-52, :71-83): asynchronous, operates on a DEVICE pointer
+ *    in the reference's local layout, completion observed with dlaf_b200_wait (= waitLocalTiles()).
+ *  * the miniapp's input generator (include/dlaf/util_matrix.h:410-453, :529-531) and result check
+ *    (miniapp/miniapp_cholesky.cpp:408-446). */
+#pragma once
+
+#include <dlaf_c/desc.h>
+#include <dlaf_c/utils.h>
+
+/* Asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream). In place when the tiles need no
+ * padding (nb a multiple of 128 (real) / 64 (complex), n a multiple of nb, even ld, 16-byte aligned). */
+DLAF_EXTERN_C int dlaf_b200_cholesky_factorization_device_s(int ctx, char uplo, float* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_cholesky_factorization_device_d(int ctx, char uplo, double* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_cholesky_factorization_device_c(int ctx, char uplo, dlaf_complex_c* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_cholesky_factorization_device_z(int ctx, char uplo, dlaf_complex_z* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+/* Synchronise the stream and return the LAPACK-style info of the last factorization issued on ctx
+ * (max over the ranks of the grid). */
+DLAF_EXTERN_C int dlaf_b200_wait(int ctx, void* cuda_stream) DLAF_NOEXCEPT;
+/* Number of this library's kernel launches issued by the last factorization on ctx. */
+DLAF_EXTERN_C long dlaf_b200_last_launch_count(int ctx) DLAF_NOEXCEPT;
+
+/* Fill this rank's HOST local part with the miniapp's random Hermitian positive definite matrix. */
+DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_s(int ctx, float* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_d(int ctx, double* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_c(int ctx, dlaf_complex_c* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_z(int ctx, dlaf_complex_z* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+
+/* Grid coordinates of this rank in ctx: out = {nprow, npcol, myprow, mypcol}. */
+DLAF_EXTERN_C void dlaf_b200_grid_info(int ctx, int out[4]) DLAF_NOEXCEPT;
+/* Rows / columns of the local part (reference: Distribution::local_size, src/matrix/distribution.cpp:117-150). */
+DLAF_EXTERN_C int dlaf_b200_local_rows(int ctx, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_local_cols(int ctx, struct DLAF_descriptor desc) DLAF_NOEXCEPT;

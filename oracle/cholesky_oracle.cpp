@@ -1,0 +1,433 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product: nothing under dla-future_b200/ may
+// include, link or call this file. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs use it, and only as the checker / CPU baseline.
+//
+// CPU restatement of the reference's Cholesky path (eth-cscs/DLA-Future v0.10.0). The reference's MC
+// backend cannot be built here (pika, blaspp, lapackpp, Umpire and MPI are REQUIRED by
+// CMakeLists.txt:164-184 and absent), so kind = "port". The arithmetic of the reference lives in the
+// vendor BLAS/LAPACK behind blaspp/lapackpp (include/dlaf/lapack/tile.h:453, include/dlaf/blas/tile.h:180,
+// :210, :243); here the same routines come from OpenBLAS 0.3.30 shipped in the scipy wheel
+// (Fortran symbols with the scipy_ prefix).
+//
+// Parity pinning: this restatement is checked against the reference's own closed-form golden
+// vectors (test/include/dlaf_test/matrix/util_generic_lapack.h:39-68, sizes of
+// test/unit/factorization/test_cholesky.cpp:54-58) in tests/test_oracle.py.
+//
+// What is restated, with the reference lines each function follows:
+//   * cholesky_local<T>()      include/dlaf/factorization/cholesky/impl.h:150-189 (call_L, local)
+//                              and :316-348 (call_U, local); tile ops :46-94 and :98-146
+//   * the tile-op DAG + pool   per-tile FIFO read/readwrite order (matrix/internal/tile_pipeline.h:36-51),
+//                              priorities impl.h:171-173, one BLAS thread per tile op
+//                              (src/common/single_threaded_blas.cpp:24-36)
+//   * set_random_hpd<T>()      include/dlaf/util_matrix.h:161-189, :335-389, :410-453, :529-531
+//   * residual<T>()            miniapp/miniapp_cholesky.cpp:408-446 (max|A-LL^H| / max|A|, lower)
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <queue>
+#include <random>
+#include <thread>
+#include <vector>
+
+extern "C" {
+void scipy_openblas_set_num_threads(int);
+int scipy_openblas_get_num_threads(void);
+char* scipy_openblas_get_config(void);
+
+#define DECL_REAL(p, T)                                                                          \
+  void scipy_##p##potrf_(const char*, const int*, T*, const int*, int*);                         \
+  void scipy_##p##trsm_(const char*, const char*, const char*, const char*, const int*,          \
+                        const int*, const T*, const T*, const int*, T*, const int*);             \
+  void scipy_##p##gemm_(const char*, const char*, const int*, const int*, const int*, const T*,  \
+                        const T*, const int*, const T*, const int*, const T*, T*, const int*);
+DECL_REAL(s, float)
+DECL_REAL(d, double)
+DECL_REAL(c, std::complex<float>)
+DECL_REAL(z, std::complex<double>)
+void scipy_ssyrk_(const char*, const char*, const int*, const int*, const float*, const float*,
+                  const int*, const float*, float*, const int*);
+void scipy_dsyrk_(const char*, const char*, const int*, const int*, const double*, const double*,
+                  const int*, const double*, double*, const int*);
+void scipy_cherk_(const char*, const char*, const int*, const int*, const float*,
+                  const std::complex<float>*, const int*, const float*, std::complex<float>*,
+                  const int*);
+void scipy_zherk_(const char*, const char*, const int*, const int*, const double*,
+                  const std::complex<double>*, const int*, const double*, std::complex<double>*,
+                  const int*);
+}
+
+namespace {
+
+template <class T>
+struct Base {
+  using type = T;
+};
+template <class T>
+struct Base<std::complex<T>> {
+  using type = T;
+};
+template <class T>
+using BaseT = typename Base<T>::type;
+
+// ---- BLAS/LAPACK dispatch -------------------------------------------------------------------
+inline int potrf(char uplo, int n, float* a, int lda) {
+  int info;
+  scipy_spotrf_(&uplo, &n, a, &lda, &info);
+  return info;
+}
+inline int potrf(char uplo, int n, double* a, int lda) {
+  int info;
+  scipy_dpotrf_(&uplo, &n, a, &lda, &info);
+  return info;
+}
+inline int potrf(char uplo, int n, std::complex<float>* a, int lda) {
+  int info;
+  scipy_cpotrf_(&uplo, &n, a, &lda, &info);
+  return info;
+}
+inline int potrf(char uplo, int n, std::complex<double>* a, int lda) {
+  int info;
+  scipy_zpotrf_(&uplo, &n, a, &lda, &info);
+  return info;
+}
+#define TRSM_IMPL(p, T)                                                                           \
+  inline void trsm(char side, char uplo, char op, char diag, int m, int n, T alpha, const T* a,   \
+                   int lda, T* b, int ldb) {                                                      \
+    scipy_##p##trsm_(&side, &uplo, &op, &diag, &m, &n, &alpha, a, &lda, b, &ldb);                 \
+  }                                                                                               \
+  inline void gemm(char opa, char opb, int m, int n, int k, T alpha, const T* a, int lda,         \
+                   const T* b, int ldb, T beta, T* c, int ldc) {                                  \
+    scipy_##p##gemm_(&opa, &opb, &m, &n, &k, &alpha, a, &lda, b, &ldb, &beta, c, &ldc);           \
+  }
+TRSM_IMPL(s, float)
+TRSM_IMPL(d, double)
+TRSM_IMPL(c, std::complex<float>)
+TRSM_IMPL(z, std::complex<double>)
+inline void herk(char uplo, char op, int n, int k, float alpha, const float* a, int lda, float beta,
+                 float* c, int ldc) {
+  scipy_ssyrk_(&uplo, &op, &n, &k, &alpha, a, &lda, &beta, c, &ldc);
+}
+inline void herk(char uplo, char op, int n, int k, double alpha, const double* a, int lda,
+                 double beta, double* c, int ldc) {
+  scipy_dsyrk_(&uplo, &op, &n, &k, &alpha, a, &lda, &beta, c, &ldc);
+}
+inline void herk(char uplo, char op, int n, int k, float alpha, const std::complex<float>* a,
+                 int lda, float beta, std::complex<float>* c, int ldc) {
+  scipy_cherk_(&uplo, &op, &n, &k, &alpha, a, &lda, &beta, c, &ldc);
+}
+inline void herk(char uplo, char op, int n, int k, double alpha, const std::complex<double>* a,
+                 int lda, double beta, std::complex<double>* c, int ldc) {
+  scipy_zherk_(&uplo, &op, &n, &k, &alpha, a, &lda, &beta, c, &ldc);
+}
+template <class T>
+constexpr char conj_trans() {
+  // For real T, ConjTrans == Trans (include/dlaf/gpu/blas/gpublas.h:107-112)
+  return std::is_same_v<T, BaseT<T>> ? 'T' : 'C';
+}
+
+// ---- tile task DAG --------------------------------------------------------------------------
+// The reference never states dependencies: they follow from the FIFO order in which read() /
+// readwrite() senders are requested from each tile (tile_pipeline.h:36-51). The same rule here:
+// a task depends on the last writer of every tile it touches, and a writer additionally on every
+// reader since that write.
+struct Task {
+  std::function<void()> fn;
+  int priority = 0;  // 1 = high (impl.h:171-173: first trailing column)
+  std::vector<int> succ;
+  std::atomic<int> deps{0};
+};
+
+class TaskGraph {
+public:
+  explicit TaskGraph(int ntiles) : last_writer_(ntiles, -1), readers_(ntiles) {}
+
+  void add(std::function<void()> fn, int priority, const std::vector<int>& reads,
+           const std::vector<int>& writes) {
+    const int id = static_cast<int>(tasks_.size());
+    tasks_.emplace_back(new Task);
+    Task& t = *tasks_.back();
+    t.fn = std::move(fn);
+    t.priority = priority;
+    std::vector<int> deps;
+    for (int tile : reads) {
+      if (last_writer_[tile] >= 0)
+        deps.push_back(last_writer_[tile]);
+      readers_[tile].push_back(id);
+    }
+    for (int tile : writes) {
+      if (last_writer_[tile] >= 0)
+        deps.push_back(last_writer_[tile]);
+      for (int r : readers_[tile])
+        if (r != id)
+          deps.push_back(r);
+      readers_[tile].clear();
+      last_writer_[tile] = id;
+    }
+    std::sort(deps.begin(), deps.end());
+    deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+    t.deps = static_cast<int>(deps.size());
+    for (int d : deps)
+      tasks_[d]->succ.push_back(id);
+  }
+
+  // Executes all tasks on nthreads workers: ready tasks by (priority, issue order).
+  void run(int nthreads) {
+    if (nthreads <= 1) {
+      for (auto& t : tasks_)
+        t->fn();  // issue order is a valid topological order
+      return;
+    }
+    using Item = std::pair<int, int>;  // (-priority, id) -> min-heap
+    std::priority_queue<Item, std::vector<Item>, std::greater<Item>> ready;
+    std::mutex m;
+    std::condition_variable cv;
+    size_t done = 0;
+    for (size_t i = 0; i < tasks_.size(); ++i)
+      if (tasks_[i]->deps == 0)
+        ready.push({-tasks_[i]->priority, static_cast<int>(i)});
+    auto worker = [&]() {
+      std::unique_lock<std::mutex> lk(m);
+      while (true) {
+        cv.wait(lk, [&] { return !ready.empty() || done == tasks_.size(); });
+        if (ready.empty())
+          return;
+        const int id = ready.top().second;
+        ready.pop();
+        lk.unlock();
+        tasks_[id]->fn();
+        lk.lock();
+        ++done;
+        for (int s : tasks_[id]->succ)
+          if (--tasks_[s]->deps == 0)
+            ready.push({-tasks_[s]->priority, s});
+        cv.notify_all();
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int i = 0; i < nthreads; ++i)
+      pool.emplace_back(worker);
+    for (auto& th : pool)
+      th.join();
+  }
+
+private:
+  std::vector<std::unique_ptr<Task>> tasks_;
+  std::vector<int> last_writer_;
+  std::vector<std::vector<int>> readers_;
+};
+
+// ---- local Cholesky, tile by tile -----------------------------------------------------------
+template <class T>
+int cholesky_local(char uplo, long n, long nb, T* a, long lda, int nthreads) {
+  if (n == 0)
+    return 0;
+  const int nt = static_cast<int>((n + nb - 1) / nb);
+  auto ts = [&](int i) { return static_cast<int>(std::min<long>(nb, n - i * nb)); };
+  auto tile = [&](int i, int j) { return a + i * nb + j * nb * lda; };
+  auto id = [&](int i, int j) { return i + j * nt; };
+  const int ld = static_cast<int>(lda);
+  const char CT = conj_trans<T>();
+  std::atomic<int> info{0};
+  TaskGraph g(nt * nt);
+  const bool lower = (uplo == 'L' || uplo == 'l');
+
+  for (int k = 0; k < nt; ++k) {
+    // potrfDiagTile (impl.h:46-53 / :98-105), high priority
+    g.add(
+        [=, &info] {
+          int r = potrf(lower ? 'L' : 'U', ts(k), tile(k, k), ld);
+          int expected = 0;
+          if (r != 0)
+            info.compare_exchange_strong(expected, k * static_cast<int>(nb) + r);
+        },
+        1, {}, {id(k, k)});
+    if (lower) {
+      for (int i = k + 1; i < nt; ++i)  // trsmPanelTile (impl.h:55-67): Right, Lower, ConjTrans, NonUnit
+        g.add([=] { trsm('R', 'L', CT, 'N', ts(i), ts(k), T(1), tile(k, k), ld, tile(i, k), ld); }, 1,
+              {id(k, k)}, {id(i, k)});
+      for (int j = k + 1; j < nt; ++j) {
+        const int prio = (j == k + 1) ? 1 : 0;  // impl.h:171-173
+        // herkTrailingDiagTile (impl.h:69-80): Lower, NoTrans, -1, 1
+        g.add([=] { herk('L', 'N', ts(j), ts(k), BaseT<T>(-1), tile(j, k), ld, BaseT<T>(1), tile(j, j), ld); },
+              prio, {id(j, k)}, {id(j, j)});
+        for (int i = j + 1; i < nt; ++i)  // gemmTrailingMatrixTile (impl.h:82-94): NoTrans, ConjTrans
+          g.add([=] { gemm('N', CT, ts(i), ts(j), ts(k), T(-1), tile(i, k), ld, tile(j, k), ld, T(1), tile(i, j), ld); },
+                prio, {id(i, k), id(j, k)}, {id(i, j)});
+      }
+    }
+    else {
+      for (int j = k + 1; j < nt; ++j)  // trsmPanelTile (impl.h:107-119): Left, Upper, ConjTrans, NonUnit
+        g.add([=] { trsm('L', 'U', CT, 'N', ts(k), ts(j), T(1), tile(k, k), ld, tile(k, j), ld); }, 1,
+              {id(k, k)}, {id(k, j)});
+      for (int i = k + 1; i < nt; ++i) {
+        const int prio = (i == k + 1) ? 1 : 0;
+        // herkTrailingDiagTile (impl.h:121-132): Upper, ConjTrans
+        g.add([=] { herk('U', CT, ts(i), ts(k), BaseT<T>(-1), tile(k, i), ld, BaseT<T>(1), tile(i, i), ld); },
+              prio, {id(k, i)}, {id(i, i)});
+        for (int j = i + 1; j < nt; ++j)  // gemmTrailingMatrixTile (impl.h:134-146): ConjTrans, NoTrans
+          g.add([=] { gemm(CT, 'N', ts(i), ts(j), ts(k), T(-1), tile(k, i), ld, tile(k, j), ld, T(1), tile(i, j), ld); },
+                prio, {id(k, i), id(k, j)}, {id(i, j)});
+      }
+    }
+  }
+  const int prev = scipy_openblas_get_num_threads();
+  scipy_openblas_set_num_threads(1);  // SingleThreadedBlasScope: one BLAS thread per tile op
+  g.run(nthreads);
+  scipy_openblas_set_num_threads(prev);
+  return info.load();
+}
+
+// ---- random Hermitian positive definite matrix ---------------------------------------------
+template <class T>
+struct Rand {  // getter_random (util_matrix.h:161-177)
+  explicit Rand(long seed) : eng(static_cast<std::size_t>(seed)) {}
+  T operator()() { return dist(eng); }
+  std::mt19937_64 eng;
+  std::uniform_real_distribution<T> dist{-1, 1};
+};
+template <class T>
+struct Rand<std::complex<T>> : Rand<T> {  // util_matrix.h:180-189
+  using Rand<T>::Rand;
+  std::complex<T> operator()() {
+    // NOTE: evaluation order of the two draws follows the argument evaluation order gcc uses for the
+    // reference expression std::polar(abs(r()), pi * r()), i.e. right-to-left: angle first, radius second.
+    T angle = static_cast<T>(M_PI) * Rand<T>::operator()();
+    T radius = std::abs(Rand<T>::operator()());
+    return std::polar<T>(radius, angle);
+  }
+};
+template <class T>
+T cj(T v) {
+  return v;
+}
+template <class T>
+std::complex<T> cj(std::complex<T> v) {
+  return std::conj(v);
+}
+template <class T>
+T from_real(BaseT<T> v) {
+  return T(v);
+}
+template <class T>
+BaseT<T> re(T v) {
+  return std::real(v);
+}
+
+template <class T>
+void set_random_hpd(long n, long nb, T* a, long lda) {
+  const long nt = (n + nb - 1) / nb;
+  const long offset = 2 * n;  // util_matrix.h:529-531
+  auto one = [&](long ti, long tj) {
+    const long r0 = ti * nb, c0 = tj * nb;
+    const long tr = std::min(nb, n - r0), tc = std::min(nb, n - c0);
+    T* t = a + r0 + c0 * lda;
+    // util_matrix.h:435-439: same seed for a tile and its transposed twin
+    const long seed = (ti >= tj) ? c0 + r0 * n : r0 + c0 * n;
+    Rand<T> rnd(seed);
+    if (ti == tj) {  // util_matrix.h:337-349
+      for (long j = 0; j < tc; ++j) {
+        for (long i = 0; i < j; ++i) {
+          T v = rnd();
+          t[i + j * lda] = v;
+          t[j + i * lda] = cj(v);
+        }
+        t[j + j * lda] = from_real<T>(re(rnd()) + BaseT<T>(offset));
+      }
+    }
+    else {  // util_matrix.h:351-389: values drawn over the FULL tile size, column-major
+      for (long j = 0; j < nb; ++j)
+        for (long i = 0; i < nb; ++i) {
+          T v = rnd();
+          if (ti > tj) {
+            if (i < tr && j < tc)
+              t[i + j * lda] = v;
+          }
+          else {
+            if (j < tr && i < tc)
+              t[j + i * lda] = cj(v);
+          }
+        }
+    }
+  };
+  std::vector<std::thread> pool;
+  std::atomic<long> next{0};
+  const int nthr = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  for (int w = 0; w < nthr; ++w)
+    pool.emplace_back([&] {
+      for (long idx; (idx = next++) < nt * nt;)
+        one(idx % nt, idx / nt);
+    });
+  for (auto& th : pool)
+    th.join();
+}
+
+// ---- miniapp residual check ---------------------------------------------------------------
+template <class T>
+double residual(char uplo, long n, const T* a, long lda, const T* f, long ldf) {
+  // max over the uplo triangle of |A - L L^H| (or |A - U^H U|) divided by max |A| over that triangle
+  // (miniapp_cholesky.cpp:414-445; the reference only checks 'L', 'U' is the mirrored statement).
+  if (n == 0)
+    return 0.0;
+  const bool lower = (uplo == 'L' || uplo == 'l');
+  std::vector<T> fac(static_cast<size_t>(n) * n, T(0));
+  for (long j = 0; j < n; ++j)
+    for (long i = 0; i < n; ++i)
+      if (lower ? i >= j : i <= j)
+        fac[i + j * n] = f[i + j * ldf];
+  std::vector<T> prod(static_cast<size_t>(n) * n);
+  const int ni = static_cast<int>(n);
+  if (lower)
+    gemm('N', conj_trans<T>(), ni, ni, ni, T(1), fac.data(), ni, fac.data(), ni, T(0), prod.data(), ni);
+  else
+    gemm(conj_trans<T>(), 'N', ni, ni, ni, T(1), fac.data(), ni, fac.data(), ni, T(0), prod.data(), ni);
+  double max_a = 0, max_d = 0;
+  for (long j = 0; j < n; ++j)
+    for (long i = 0; i < n; ++i)
+      if (lower ? i >= j : i <= j) {
+        max_a = std::max<double>(max_a, std::abs(a[i + j * lda]));
+        max_d = std::max<double>(max_d, std::abs(a[i + j * lda] - prod[i + j * n]));
+      }
+  return max_d / max_a;
+}
+
+}  // namespace
+
+#define EXPORT_TYPE(sfx, T)                                                                      \
+  extern "C" int oracle_cholesky_local_##sfx(char uplo, long n, long nb, void* a, long lda,      \
+                                             int nthreads) {                                     \
+    return cholesky_local<T>(uplo, n, nb, static_cast<T*>(a), lda, nthreads);                    \
+  }                                                                                              \
+  extern "C" int oracle_lapack_potrf_##sfx(char uplo, long n, void* a, long lda, int nthreads) { \
+    const int prev = scipy_openblas_get_num_threads();                                           \
+    scipy_openblas_set_num_threads(nthreads);                                                    \
+    int info = potrf(uplo, static_cast<int>(n), static_cast<T*>(a), static_cast<int>(lda));      \
+    scipy_openblas_set_num_threads(prev);                                                        \
+    return info;                                                                                 \
+  }                                                                                              \
+  extern "C" void oracle_set_random_hpd_##sfx(long n, long nb, void* a, long lda) {              \
+    set_random_hpd<T>(n, nb, static_cast<T*>(a), lda);                                           \
+  }                                                                                              \
+  extern "C" double oracle_residual_##sfx(char uplo, long n, const void* a, long lda,            \
+                                          const void* f, long ldf) {                             \
+    return residual<T>(uplo, n, static_cast<const T*>(a), lda, static_cast<const T*>(f), ldf);   \
+  }
+
+EXPORT_TYPE(s, float)
+EXPORT_TYPE(d, double)
+EXPORT_TYPE(c, std::complex<float>)
+EXPORT_TYPE(z, std::complex<double>)
+
+extern "C" const char* oracle_blas_config() {
+  return scipy_openblas_get_config();
+}
+extern "C" int oracle_hardware_threads() {
+  return static_cast<int>(std::thread::hardware_concurrency());
+}

@@ -1,0 +1,261 @@
+"""dla-future_b200 — Python face of the B200-native POTRF library (ctypes over the C ABI).
+
+The product is `lib/libdlaf_b200.so` (hand-written sm_100a kernels + C++ stream scheduler + NCCL grid),
+whose exported symbols are the reference's C API for this path (include/dlaf_c/*.h). This module only
+binds them the way a host language would; it contains no compute and NO fallback:
+if the shared library is missing or no GPU is present, calls fail loudly.
+
+Because the directory name carries a hyphen it is imported through `__graft_entry__.load_package()`
+(registered in sys.modules as `dlaf_b200`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "lib", "libdlaf_b200.so")
+
+TYPES = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+
+# every symbol include/dlaf_c/*.h declares
+C_API_SYMBOLS = [
+    "dlaf_initialize", "dlaf_finalize",
+    "dlaf_create_grid", "dlaf_free_grid", "dlaf_free_all_grids", "grid_ordering",
+    "dlaf_b200_get_unique_id", "dlaf_b200_comm_create", "dlaf_b200_comm_destroy",
+    "make_dlaf_descriptor",
+    *[f"dlaf_cholesky_factorization_{t}" for t in "sdcz"],
+    *[f"dlaf_p{t}potrf" for t in "sdcz"],
+    *[f"dlaf_b200_cholesky_factorization_device_{t}" for t in "sdcz"],
+    *[f"dlaf_b200_set_random_hermitian_positive_definite_{t}" for t in "sdcz"],
+    "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info",
+    "dlaf_b200_local_rows", "dlaf_b200_local_cols",
+]
+
+
+class DLAF_descriptor(ctypes.Structure):
+    """struct DLAF_descriptor (include/dlaf_c/desc.h; reference include/dlaf_c/desc.h:16-26)."""
+    _fields_ = [(k, ctypes.c_int) for k in ("m", "n", "mb", "nb", "isrc", "jsrc", "i", "j", "ld")]
+
+
+def build(force: bool = False) -> str:
+    """Compile the shared library in-tree with nvcc for sm_100a (make). Returns its path."""
+    if force or not os.path.exists(LIB_PATH) or _stale():
+        subprocess.check_call(["make", "-C", _ROOT, "-j8", os.path.relpath(LIB_PATH, _ROOT)])
+    return LIB_PATH
+
+
+def _stale() -> bool:
+    t = os.path.getmtime(LIB_PATH)
+    src = os.path.join(_HERE, "csrc")
+    inc = os.path.join(_ROOT, "include", "dlaf_c")
+    for d in (src, inc, os.path.join(inc, "factorization")):
+        for f in os.listdir(d):
+            p = os.path.join(d, f)
+            if os.path.isfile(p) and os.path.getmtime(p) > t:
+                return True
+    return False
+
+
+_lib = None
+
+
+def _preload_nccl() -> None:
+    """libdlaf_b200.so needs libnccl.so.2. In a process that also imports torch, both must resolve to
+    the SAME NCCL (torch's bundled one is newer than the system's and torch needs its symbols), so the
+    bundled library is loaded first when it exists; a plain C/C++ host uses the system libnccl."""
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            cand = os.path.join(list(spec.submodule_search_locations)[0], "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                ctypes.CDLL(cand, mode=ctypes.RTLD_GLOBAL)
+    except Exception:  # the system libnccl.so.2 (NEEDED entry) is the fallback
+        pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load the C-ABI library (no compute happens at load time, so this works without a GPU)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a) first. "
+                           "There is no CPU or PyTorch fallback.")
+    _preload_nccl()
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cc = ctypes.c_void_p, ctypes.c_int, ctypes.c_char
+    L.dlaf_initialize.argtypes = [ci, ctypes.POINTER(ctypes.c_char_p), ci, ctypes.POINTER(ctypes.c_char_p)]
+    L.dlaf_initialize.restype = None
+    L.dlaf_finalize.restype = None
+    L.dlaf_create_grid.argtypes = [vp, ci, ci, cc]
+    L.dlaf_create_grid.restype = ci
+    L.dlaf_free_grid.argtypes = [ci]
+    L.dlaf_free_grid.restype = None
+    L.dlaf_free_all_grids.restype = None
+    L.grid_ordering.argtypes = [vp, ci, ci, ci, ci]
+    L.grid_ordering.restype = cc
+    L.dlaf_b200_get_unique_id.argtypes = [vp]
+    L.dlaf_b200_get_unique_id.restype = None
+    L.dlaf_b200_comm_create.argtypes = [vp, ci, ci]
+    L.dlaf_b200_comm_create.restype = vp
+    L.dlaf_b200_comm_destroy.argtypes = [vp]
+    L.dlaf_b200_comm_destroy.restype = None
+    L.make_dlaf_descriptor.argtypes = [ci, ci, ci, ci, ctypes.POINTER(ci)]
+    L.make_dlaf_descriptor.restype = DLAF_descriptor
+    for t in "sdcz":
+        f = getattr(L, f"dlaf_cholesky_factorization_{t}", None)
+        if f is None:
+            continue
+        f.argtypes = [ci, cc, vp, DLAF_descriptor]
+        f.restype = ci
+        f = getattr(L, f"dlaf_p{t}potrf")
+        f.argtypes = [cc, ci, vp, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        f.restype = None
+        f = getattr(L, f"dlaf_b200_cholesky_factorization_device_{t}")
+        f.argtypes = [ci, cc, vp, DLAF_descriptor, vp]
+        f.restype = ci
+        f = getattr(L, f"dlaf_b200_set_random_hermitian_positive_definite_{t}")
+        f.argtypes = [ci, vp, DLAF_descriptor]
+        f.restype = None
+    L.dlaf_b200_wait.argtypes = [ci, vp]
+    L.dlaf_b200_wait.restype = ci
+    L.dlaf_b200_last_launch_count.argtypes = [ci]
+    L.dlaf_b200_last_launch_count.restype = ctypes.c_long
+    L.dlaf_b200_grid_info.argtypes = [ci, ctypes.POINTER(ci)]
+    L.dlaf_b200_grid_info.restype = None
+    L.dlaf_b200_local_rows.argtypes = [ci, DLAF_descriptor]
+    L.dlaf_b200_local_rows.restype = ci
+    L.dlaf_b200_local_cols.argtypes = [ci, DLAF_descriptor]
+    L.dlaf_b200_local_cols.restype = ci
+    _lib = L
+    return L
+
+
+def type_char(dtype) -> str:
+    dtype = np.dtype(dtype)
+    for k, v in TYPES.items():
+        if np.dtype(v) == dtype:
+            return k
+    raise TypeError(f"unsupported element type {dtype}: the reference instantiates s, d, c, z only")
+
+
+def initialize(*dlaf_args: str) -> None:
+    """dlaf_initialize (include/dlaf_c/init.h). `dlaf_args` like '--dlaf:print-config'."""
+    args = [b"dlaf"] + [a.encode() for a in dlaf_args]
+    arr = (ctypes.c_char_p * len(args))(*args)
+    lib().dlaf_initialize(0, None, len(args), arr)
+
+
+def finalize() -> None:
+    lib().dlaf_finalize()
+
+
+def get_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    lib().dlaf_b200_get_unique_id(buf)
+    return buf.raw
+
+
+def comm_create(unique_id: bytes, rank: int, nranks: int):
+    return lib().dlaf_b200_comm_create(ctypes.c_char_p(unique_id), rank, nranks)
+
+
+def comm_create_from_torch():
+    """Bootstrap the NCCL world communicator of this process from an initialised torch.distributed
+    group (the unique id travels over the existing rendezvous). Returns the opaque DLAF_Comm."""
+    import torch.distributed as dist
+
+    rank, size = dist.get_rank(), dist.get_world_size()
+    obj = [get_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    return comm_create(obj[0], rank, size)
+
+
+def create_grid(comm, nprow: int, npcol: int, order: str = "R") -> int:
+    return lib().dlaf_create_grid(comm, nprow, npcol, order.encode())
+
+
+def free_grid(ctx: int) -> None:
+    lib().dlaf_free_grid(ctx)
+
+
+def descriptor(n: int, nb: int, ld: int, isrc: int = 0, jsrc: int = 0) -> DLAF_descriptor:
+    return DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, ld))
+
+
+def grid_info(ctx: int):
+    out = (ctypes.c_int * 4)()
+    lib().dlaf_b200_grid_info(ctx, out)
+    return tuple(out)
+
+
+def local_shape(ctx: int, desc: DLAF_descriptor):
+    return lib().dlaf_b200_local_rows(ctx, desc), lib().dlaf_b200_local_cols(ctx, desc)
+
+
+def _ld_of(a: np.ndarray) -> int:
+    assert a.ndim == 2 and (a.flags.f_contiguous or a.shape[1] <= 1 or a.strides[0] == a.itemsize), \
+        "column-major local matrix expected"
+    return max(1, a.strides[1] // a.itemsize) if a.shape[1] > 1 else max(1, a.shape[0])
+
+
+def cholesky_factorization(ctx: int, uplo: str, a: np.ndarray, nb: int, n: int | None = None,
+                           isrc: int = 0, jsrc: int = 0) -> int:
+    """dlaf_cholesky_factorization_{s,d,c,z}: `a` is this rank's HOST local part (column-major numpy
+    array), factorised in place in the `uplo` triangle. Returns info (0 = ok)."""
+    n = a.shape[0] if n is None else n
+    d = descriptor(n, nb, _ld_of(a), isrc, jsrc)
+    f = getattr(lib(), f"dlaf_cholesky_factorization_{type_char(a.dtype)}")
+    return f(ctx, uplo.encode(), a.ctypes.data, d)
+
+
+def ppotrf(ctx: int, uplo: str, a: np.ndarray, nb: int, n: int | None = None, isrc: int = 0,
+           jsrc: int = 0) -> int:
+    """dlaf_p{s,d,c,z}potrf with a ScaLAPACK descriptor {1, ctxt, m, n, mb, nb, rsrc, csrc, lld}."""
+    n = a.shape[0] if n is None else n
+    desca = (ctypes.c_int * 9)(1, ctx, n, n, nb, nb, isrc, jsrc, _ld_of(a))
+    info = ctypes.c_int(-1)
+    f = getattr(lib(), f"dlaf_p{type_char(a.dtype)}potrf")
+    f(uplo.encode(), n, a.ctypes.data, 1, 1, desca, ctypes.byref(info))
+    return info.value
+
+
+def cholesky_factorization_device(ctx: int, uplo: str, dev_ptr: int, dtype, n: int, nb: int, ld: int,
+                                  stream: int = 0, isrc: int = 0, jsrc: int = 0) -> None:
+    """Asynchronous factorization of a device-resident local part (the reference's C++
+    cholesky_factorization<Backend::GPU, Device::GPU, T>). Pair with `wait`."""
+    d = descriptor(n, nb, ld, isrc, jsrc)
+    f = getattr(lib(), f"dlaf_b200_cholesky_factorization_device_{type_char(dtype)}")
+    f(ctx, uplo.encode(), ctypes.c_void_p(dev_ptr), d, ctypes.c_void_p(stream))
+
+
+def wait(ctx: int, stream: int = 0) -> int:
+    return lib().dlaf_b200_wait(ctx, ctypes.c_void_p(stream))
+
+
+def last_launch_count(ctx: int) -> int:
+    return lib().dlaf_b200_last_launch_count(ctx)
+
+
+def set_random_hermitian_positive_definite(ctx: int, a: np.ndarray, n: int, nb: int, isrc: int = 0,
+                                           jsrc: int = 0) -> None:
+    """Fill the host local part `a` with the miniapp's input (include/dlaf/util_matrix.h:410-453)."""
+    d = descriptor(n, nb, _ld_of(a), isrc, jsrc)
+    f = getattr(lib(), f"dlaf_b200_set_random_hermitian_positive_definite_{type_char(a.dtype)}")
+    f(ctx, a.ctypes.data, d)
+
+
+def total_ops(dtype, n: int) -> float:
+    """Flop model of the miniapp: real n^3/3, complex 4 n^3/3 (miniapp_cholesky.cpp:157-162,
+    include/dlaf/types.h:121-132, :159-162)."""
+    add_mul = float(n) ** 3 / 6
+    if np.dtype(dtype).kind == "c":
+        return 2 * add_mul + 6 * add_mul
+    return 2 * add_mul

@@ -78,6 +78,8 @@ std::map<int, std::unique_ptr<GridCtx>> g_grids;  // unsynchronised like src/c_a
 int g_next_ctx = INT_MAX;
 bool g_initialized = false;
 int g_device = -1;
+int g_device_request = -1;
+bool g_print_config = false;
 
 template <class T>
 struct TypeIndex;
@@ -101,6 +103,39 @@ struct TypeIndex<std::complex<double>> {
 void ensure_initialized() {
   if (!g_initialized)
     dlaf_initialize(0, nullptr, 0, nullptr);
+}
+
+// Binds this process to its CUDA device. There is NO CPU path: without a device every compute entry
+// point aborts here.
+void ensure_device() {
+  ensure_initialized();
+  if (g_device >= 0) {
+    DLAF_CUDA_CHECK(cudaSetDevice(g_device));
+    return;
+  }
+  int ndev = 0;
+  const cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    std::fprintf(stderr, "[dlaf_b200] no CUDA device available (%s): this library has no CPU path\n",
+                 cudaGetErrorString(e));
+    std::fflush(stderr);
+    std::abort();
+  }
+  int device = g_device_request < 0 ? 0 : g_device_request % ndev;
+  DLAF_CUDA_CHECK(cudaSetDevice(device));
+  g_device = device;
+  if (g_print_config) {
+    cudaDeviceProp p;
+    DLAF_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    std::printf("dlaf_b200 configuration:\n  device = %d (%s, sm_%d%d, %d SMs)\n  granularity = 128 (real) / 64 (complex)\n",
+                device, p.name, p.major, p.minor, p.multiProcessorCount);
+  }
+}
+
+cudaStream_t ctx_stream(GridCtx& c) {
+  if (!c.stream)
+    DLAF_CUDA_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  return c.stream;
 }
 
 GridCtx& grid_from_context(int ctx) {
@@ -254,7 +289,7 @@ int reduce_info(GridCtx& c, int info, cudaStream_t s) {
 template <class T>
 int cholesky_host(int ctx, char uplo, T* a, const DLAF_descriptor& desc) {
   using D = devtype_t<T>;
-  ensure_initialized();
+  ensure_device();
   GridCtx& c = grid_from_context(ctx);
   if (!c.grid->in_grid)
     return 0;
@@ -265,7 +300,7 @@ int cholesky_host(int ctx, char uplo, T* a, const DLAF_descriptor& desc) {
   PotrfEngine<D>& eng = *slot.eng;
   eng.unbind_external();
   D* host = reinterpret_cast<D*>(a);
-  cudaStream_t s = c.stream;
+  cudaStream_t s = ctx_stream(c);
   if (u.n > 0 && u.lrows > 0 && u.lcols > 0) {
     if (!upper && !eng.padded()) {
       // tiles need no padding: the slab IS the user layout, copy straight into it
@@ -294,7 +329,7 @@ int cholesky_host(int ctx, char uplo, T* a, const DLAF_descriptor& desc) {
 template <class T>
 int cholesky_device(int ctx, char uplo, T* a_dev, const DLAF_descriptor& desc, void* stream) {
   using D = devtype_t<T>;
-  ensure_initialized();
+  ensure_device();
   GridCtx& c = grid_from_context(ctx);
   if (!c.grid->in_grid)
     return 0;
@@ -352,39 +387,20 @@ extern "C" {
 void dlaf_initialize(int, const char**, int argc_dlaf, const char** argv_dlaf) noexcept {
   if (g_initialized)
     return;
-  int device = -1;
-  bool print_config = false;
   if (const char* e = std::getenv("DLAF_B200_DEVICE"))
-    device = std::atoi(e);
+    g_device_request = std::atoi(e);
   else if (const char* e2 = std::getenv("LOCAL_RANK"))
-    device = std::atoi(e2);
+    g_device_request = std::atoi(e2);
   for (int i = 0; i < argc_dlaf; ++i) {
     const std::string arg = argv_dlaf[i] ? argv_dlaf[i] : "";
     if (arg.rfind("--dlaf:device=", 0) == 0)
-      device = std::atoi(arg.c_str() + 14);
+      g_device_request = std::atoi(arg.c_str() + 14);
     else if (arg == "--dlaf:print-config")
-      print_config = true;
-  }
-  int ndev = 0;
-  const cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0) {
-    std::fprintf(stderr, "[dlaf_b200] no CUDA device available (%s): this library has no CPU path\n",
-                 cudaGetErrorString(e));
-    std::fflush(stderr);
-    std::abort();
-  }
-  if (device < 0)
-    device = 0;
-  device %= ndev;
-  DLAF_CUDA_CHECK(cudaSetDevice(device));
-  g_device = device;
-  if (print_config) {
-    cudaDeviceProp p;
-    DLAF_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
-    std::printf("dlaf_b200 configuration:\n  device = %d (%s, sm_%d%d, %d SMs)\n  granularity = 128 (real) / 64 (complex)\n",
-                device, p.name, p.major, p.minor, p.multiProcessorCount);
+      g_print_config = true;
   }
   g_initialized = true;
+  // The device itself is bound at the first call that needs it (ensure_device): grids, descriptors
+  // and the host-side input generator work without one.
 }
 
 void dlaf_finalize(void) noexcept {
@@ -392,6 +408,7 @@ void dlaf_finalize(void) noexcept {
     return;
   g_grids.clear();
   g_initialized = false;
+  g_device = -1;
 }
 
 void dlaf_b200_get_unique_id(void* id128) noexcept {
@@ -402,7 +419,7 @@ void dlaf_b200_get_unique_id(void* id128) noexcept {
 }
 
 struct dlaf_b200_comm* dlaf_b200_comm_create(const void* id128, int rank, int nranks) noexcept {
-  ensure_initialized();
+  ensure_device();
   return comm_create(id128, rank, nranks);
 }
 
@@ -414,7 +431,6 @@ int dlaf_create_grid(DLAF_Comm comm, int nprow, int npcol, char order) noexcept 
   ensure_initialized();
   std::unique_ptr<GridCtx> c(new GridCtx);
   c->grid.reset(new CommGrid(comm, nprow, npcol, order));
-  DLAF_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   const int ctx = g_next_ctx--;
   g_grids[ctx] = std::move(c);
   return ctx;
@@ -463,11 +479,9 @@ struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int 
   }
 
 DLAF_B200_DEFINE(d, double)
-#ifdef DLAF_B200_ALL_TYPES
 DLAF_B200_DEFINE(s, float)
 DLAF_B200_DEFINE(c, dlaf_complex_c)
 DLAF_B200_DEFINE(z, dlaf_complex_z)
-#endif
 
 int dlaf_b200_wait(int ctx, void* stream) noexcept {
   GridCtx& c = grid_from_context(ctx);

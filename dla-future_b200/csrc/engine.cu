@@ -442,6 +442,9 @@ int PotrfEngine<T>::info(cudaStream_t s) {
   return v;
 }
 
+template class PotrfEngine<float>;
 template class PotrfEngine<double>;
+template class PotrfEngine<float2>;
+template class PotrfEngine<double2>;
 
 }  // namespace dlaf_b200

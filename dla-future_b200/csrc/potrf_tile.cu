@@ -1,140 +1,201 @@
-// See potrf_tile.cuh. Algorithm (validated against numpy in tools/proto_potrf_inv.py):
+// See potrf_tile.cuh. Algorithm (validated against numpy in tools/proto_potrf_inv*.py):
 //
-// The 128x128 block lives in shared memory as S (column-major, odd leading dimension so both
+// The G x G block lives in shared memory as S (column-major, odd leading dimension so both
 // S(r, c) with r running and S(c, r) with r running are bank-conflict free). The lower triangle
-// holds A -> L. The strictly upper triangle holds M^T where M converges to inv(L): applying the
+// holds A -> L. The strictly upper triangle holds M^H where M converges to inv(L): applying the
 // elementary eliminations L_j^-1 to the identity is, element for element, the SAME rank-1 rule as
 // the right-looking Cholesky update:
 //
 //     for column j:   d = sqrt(S(j,j));  S(:,j) /= d  (all rows but j)
-//                     for s > j, for r with (r >= s) or (r < j):   S(r,s) -= S(r,j) * S(s,j)
-//                     S(j,s) = -S(s,j) / d                                   (new M(s,j))
+//                     for s > j, for r with (r >= s) or (r < j):   S(r,s) -= S(r,j) * conj(S(s,j))
+//                     S(j,s) = -conj(S(s,j)) / d                             (new conj(M(s,j)))
 //
 // so one sweep with two barriers per column yields both L and inv(L).
 #include "potrf_tile.cuh"
 
 #include "common.h"
+#include "types.h"
 
 namespace dlaf_b200 {
 
 namespace {
 
-constexpr int PB = kPotrfBlock;
-constexpr int PLD = PB + 1;
 constexpr int kPotrfThreads = 256;
-constexpr int kPotrfSmem = (PB * PLD + 2 * PB) * 8;
 
+// ---- element arithmetic -----------------------------------------------------------------------
+__device__ __forceinline__ float re_of(float v) { return v; }
+__device__ __forceinline__ double re_of(double v) { return v; }
+__device__ __forceinline__ float re_of(float2 v) { return v.x; }
+__device__ __forceinline__ double re_of(double2 v) { return v.x; }
+
+__device__ __forceinline__ float scale_r(float v, float s) { return v * s; }
+__device__ __forceinline__ double scale_r(double v, double s) { return v * s; }
+__device__ __forceinline__ float2 scale_r(float2 v, float s) { return make_float2(v.x * s, v.y * s); }
+__device__ __forceinline__ double2 scale_r(double2 v, double s) { return make_double2(v.x * s, v.y * s); }
+
+// v - a * conj(b)
+__device__ __forceinline__ float sub_mul_conj(float v, float a, float b) { return fmaf(-a, b, v); }
+__device__ __forceinline__ double sub_mul_conj(double v, double a, double b) { return fma(-a, b, v); }
+__device__ __forceinline__ float2 sub_mul_conj(float2 v, float2 a, float2 b) {
+  return make_float2(fmaf(-a.y, b.y, fmaf(-a.x, b.x, v.x)), fmaf(a.x, b.y, fmaf(-a.y, b.x, v.y)));
+}
+__device__ __forceinline__ double2 sub_mul_conj(double2 v, double2 a, double2 b) {
+  return make_double2(fma(-a.y, b.y, fma(-a.x, b.x, v.x)), fma(a.x, b.y, fma(-a.y, b.x, v.y)));
+}
+
+__device__ __forceinline__ float neg(float v) { return -v; }
+__device__ __forceinline__ double neg(double v) { return -v; }
+__device__ __forceinline__ float2 neg(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ double2 neg(double2 v) { return make_double2(-v.x, -v.y); }
+
+// reciprocal square root: hardware estimate + one Newton step (~1 ulp)
+__device__ __forceinline__ float fast_rsqrt(float a) {
+  float y = rsqrtf(a);
+  return fmaf(y * 0.5f, fmaf(-a * y, y, 1.0f), y);
+}
+__device__ __forceinline__ double fast_rsqrt(double a) {
+  double y = rsqrt(a);
+  return fma(y * 0.5, fma(-a * y, y, 1.0), y);
+}
+__device__ __forceinline__ float full_sqrt(float a) { return sqrtf(a); }
+__device__ __forceinline__ double full_sqrt(double a) { return sqrt(a); }
+
+template <class T>
+__device__ __forceinline__ T zero_of() {
+  return make_real<T>(0);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <class T, int PB>
 __global__ void __launch_bounds__(kPotrfThreads, 1)
-    potrf128_inv_f64_kernel(double* __restrict__ T, long ldt, double* __restrict__ W, long ldw,
-                            int* info, int info_offset) {
-  extern __shared__ double S[];
-  double* dd = S + PB * PLD;  // L diagonal
-  double* dinv = dd + PB;     // 1 / L diagonal = diag(inv(L))
+    potrf_inv_kernel(T* __restrict__ Tm, long ldt, T* __restrict__ W, long ldw, int* info, int info_offset) {
+  using R = base_t<T>;
+  constexpr int PLD = PB + 1;
+  constexpr int NG = kPotrfThreads / PB;  // column groups working in parallel
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* S = reinterpret_cast<T*>(smem_raw);
+  R* dd = reinterpret_cast<R*>(S + PB * PLD);  // diag(L)
+  R* dinv = dd + PB;                           // diag(inv(L))
   const int tid = threadIdx.x;
 
   for (int idx = tid; idx < PB * PB; idx += kPotrfThreads) {
-    const int r = idx & (PB - 1), c = idx >> 7;
-    S[c * PLD + r] = (r >= c) ? T[r + c * ldt] : 0.0;
+    const int r = idx % PB, c = idx / PB;
+    S[c * PLD + r] = (r >= c) ? Tm[r + c * ldt] : zero_of<T>();
   }
   __syncthreads();
 
-  const int r = tid & (PB - 1), half = tid >> 7;
+  const int r = tid % PB, grp = tid / PB;
   int fail = 0;
   for (int j = 0; j < PB; ++j) {
-    const double ajj = S[j * PLD + j];  // nobody writes S(j,j) during or after step j
-    if (!(ajj > 0.0)) {                 // also catches NaN; uniform across the CTA
+    const R ajj = re_of(S[j * PLD + j]);  // nobody writes S(j,j) during or after step j
+    if (!(ajj > R(0))) {                  // also catches NaN; uniform across the CTA
       fail = j + 1;
       break;
     }
-    // Only the reciprocal is on the critical path: rsqrt + one Newton step (correct to ~1 ulp); the
-    // diagonal entry itself is the correctly rounded sqrt, computed by its owner thread only.
-    double inv_d = rsqrt(ajj);
-    inv_d = fma(inv_d * 0.5, fma(-ajj * inv_d, inv_d, 1.0), inv_d);
-    if (half == 0) {
+    // Only the reciprocal is on the critical path; the diagonal entry itself is the correctly rounded
+    // sqrt, computed by its owner thread only.
+    const R inv_d = fast_rsqrt(ajj);
+    if (grp == 0) {
       if (r == j) {
-        dd[j] = sqrt(ajj);
+        dd[j] = full_sqrt(ajj);
         dinv[j] = inv_d;
       }
       else {
-        S[j * PLD + r] *= inv_d;
+        S[j * PLD + r] = scale_r(S[j * PLD + r], inv_d);
       }
     }
     __syncthreads();
-    const double* colj = S + j * PLD;
+    const T* colj = S + j * PLD;
     if (r == j) {
-      for (int s = j + 1 + half; s < PB; s += 2)
-        S[s * PLD + j] = -colj[s] * inv_d;
+      for (int s = j + 1 + grp; s < PB; s += NG)
+        S[s * PLD + j] = scale_r(neg(conj_val(colj[s])), inv_d);
     }
     else {
       // rows above the pivot (inverse part) see every remaining column; rows below (Cholesky part)
       // only columns up to their own index.
       const int s_end = (r < j) ? PB : r + 1;
-      const double srj = colj[r];
-      double* col = S + r;
-      int s = j + 1 + half;
-      for (; s + 6 < s_end; s += 8) {
-        const double b0 = colj[s], b1 = colj[s + 2], b2 = colj[s + 4], b3 = colj[s + 6];
-        double v0 = col[s * PLD], v1 = col[(s + 2) * PLD], v2 = col[(s + 4) * PLD],
-               v3 = col[(s + 6) * PLD];
-        v0 = fma(-srj, b0, v0);
-        v1 = fma(-srj, b1, v1);
-        v2 = fma(-srj, b2, v2);
-        v3 = fma(-srj, b3, v3);
+      const T srj = colj[r];
+      T* col = S + r;
+      int s = j + 1 + grp;
+      for (; s + 3 * NG < s_end; s += 4 * NG) {
+        const T b0 = colj[s], b1 = colj[s + NG], b2 = colj[s + 2 * NG], b3 = colj[s + 3 * NG];
+        T v0 = col[s * PLD], v1 = col[(s + NG) * PLD], v2 = col[(s + 2 * NG) * PLD],
+          v3 = col[(s + 3 * NG) * PLD];
+        v0 = sub_mul_conj(v0, srj, b0);
+        v1 = sub_mul_conj(v1, srj, b1);
+        v2 = sub_mul_conj(v2, srj, b2);
+        v3 = sub_mul_conj(v3, srj, b3);
         col[s * PLD] = v0;
-        col[(s + 2) * PLD] = v1;
-        col[(s + 4) * PLD] = v2;
-        col[(s + 6) * PLD] = v3;
+        col[(s + NG) * PLD] = v1;
+        col[(s + 2 * NG) * PLD] = v2;
+        col[(s + 3 * NG) * PLD] = v3;
       }
-      for (; s < s_end; s += 2)
-        col[s * PLD] = fma(-srj, colj[s], col[s * PLD]);
+      for (; s < s_end; s += NG)
+        col[s * PLD] = sub_mul_conj(col[s * PLD], srj, colj[s]);
     }
     __syncthreads();
   }
   if (fail) {
     if (tid == 0)
       atomicCAS(info, 0, info_offset + fail);
-    // Leave T untouched past the failure like a trapped reference run would; W gets zeros so that
-    // downstream GEMMs stay finite.
+    // Leave T as it is past the failure (a trapped reference run would not have produced a result
+    // either); W gets zeros so that downstream GEMMs stay finite.
     for (int idx = tid; idx < PB * PB; idx += kPotrfThreads)
-      W[(idx & (PB - 1)) + (idx >> 7) * ldw] = 0.0;
+      W[(idx % PB) + (idx / PB) * ldw] = zero_of<T>();
     return;
   }
 
   for (int idx = tid; idx < PB * PB; idx += kPotrfThreads) {
-    const int rr = idx & (PB - 1), c = idx >> 7;
+    const int rr = idx % PB, c = idx / PB;
     if (rr > c) {
-      T[rr + c * ldt] = S[c * PLD + rr];
-      W[rr + c * ldw] = S[rr * PLD + c];  // M(rr,c) is stored transposed at S(c,rr)
+      Tm[rr + c * ldt] = S[c * PLD + rr];
+      W[rr + c * ldw] = conj_val(S[rr * PLD + c]);  // conj(M(rr,c)) is stored at S(c,rr)
     }
     else if (rr == c) {
-      T[rr + c * ldt] = dd[rr];
-      W[rr + c * ldw] = dinv[rr];
+      Tm[rr + c * ldt] = make_real<T>(dd[rr]);
+      W[rr + c * ldw] = make_real<T>(dinv[rr]);
     }
     else {
-      W[rr + c * ldw] = 0.0;
+      W[rr + c * ldw] = zero_of<T>();
     }
   }
+}
+
+template <class T>
+void launch_impl(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
+  constexpr int PB = Gran<T>::value;
+  constexpr int smem = (PB * (PB + 1)) * sizeof(T) + 2 * PB * sizeof(base_t<T>);
+  static bool configured = false;
+  if (!configured) {
+    DLAF_CUDA_CHECK(cudaFuncSetAttribute(potrf_inv_kernel<T, PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  potrf_inv_kernel<T, PB><<<1, kPotrfThreads, smem, stream>>>(t, ldt, w, ldw, info, info_offset);
+  DLAF_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace
 
 void launch_potrf128_inv_f64(double* T, long ldt, double* W, long ldw, int* info, int info_offset,
                              cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    DLAF_CUDA_CHECK(cudaFuncSetAttribute(potrf128_inv_f64_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem));
-    configured = true;
-  }
-  potrf128_inv_f64_kernel<<<1, kPotrfThreads, kPotrfSmem, stream>>>(T, ldt, W, ldw, info,
-                                                                    info_offset);
-  DLAF_CUDA_CHECK(cudaGetLastError());
+  launch_impl<double>(T, ldt, W, ldw, info, info_offset, stream);
 }
 
 template <>
-void launch_potrf_inv<double>(double* t, long ldt, double* w, long ldw, int* info, int info_offset,
-                              cudaStream_t stream) {
-  launch_potrf128_inv_f64(t, ldt, w, ldw, info, info_offset, stream);
+void launch_potrf_inv<double>(double* t, long ldt, double* w, long ldw, int* info, int info_offset, cudaStream_t s) {
+  launch_impl<double>(t, ldt, w, ldw, info, info_offset, s);
+}
+template <>
+void launch_potrf_inv<float>(float* t, long ldt, float* w, long ldw, int* info, int info_offset, cudaStream_t s) {
+  launch_impl<float>(t, ldt, w, ldw, info, info_offset, s);
+}
+template <>
+void launch_potrf_inv<float2>(float2* t, long ldt, float2* w, long ldw, int* info, int info_offset, cudaStream_t s) {
+  launch_impl<float2>(t, ldt, w, ldw, info, info_offset, s);
+}
+template <>
+void launch_potrf_inv<double2>(double2* t, long ldt, double2* w, long ldw, int* info, int info_offset, cudaStream_t s) {
+  launch_impl<double2>(t, ldt, w, ldw, info, info_offset, s);
 }
 
 }  // namespace dlaf_b200

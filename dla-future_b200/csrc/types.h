@@ -71,6 +71,19 @@ __host__ __device__ inline double2 conj_val(double2 v) {
   return make_double2(v.x, -v.y);
 }
 
+__host__ __device__ inline float re_part(float v) {
+  return v;
+}
+__host__ __device__ inline double re_part(double v) {
+  return v;
+}
+__host__ __device__ inline float re_part(float2 v) {
+  return v.x;
+}
+__host__ __device__ inline double re_part(double2 v) {
+  return v.x;
+}
+
 template <class T>
 __host__ __device__ inline T make_real(base_t<T> v);
 template <>

@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — POTRF GFLOP/s (fp64, N=32768, nb=512) on 1/2/4/8 B200, the metric of BASELINE.json.
+
+A "step" is one Cholesky factorization of the miniapp's random Hermitian positive definite matrix
+(include/dlaf/util_matrix.h:410-453), timed like miniapp_cholesky.cpp:137-154 (input resident on the
+device, factorization + all inter-GPU traffic + final drain), flop model N^3/3 (miniapp_cholesky.cpp:157-162).
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm (N>1: under torchrun, one rank per GPU)
+  python bench.py --impl reference --steps K --warmup W    the reference algorithm on the host cores (oracle port)
+
+One JSON line on stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "POTRF GFLOP/s (fp64, N=32768, nb=512)"
+GRIDS = {1: (1, 1), 2: (2, 1), 4: (2, 2), 8: (2, 4)}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--n", type=int, default=32768, help="matrix size (BASELINE metric: 32768)")
+    p.add_argument("--nb", type=int, default=512, help="block size (BASELINE metric: 512)")
+    p.add_argument("--grid-rows", type=int, default=0)
+    p.add_argument("--grid-cols", type=int, default=0)
+    p.add_argument("--e2e-steps", type=int, default=-1, help="end-to-end (host buffer) steps, default min(steps, 2)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-check", action="store_true")
+    p.add_argument("--cpu-sample-n", type=int, default=0, help="force the CPU sample size")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) >= 8:
+                        self.rows.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(O, n: int, nb: int, threads: int, steps: int, warmup: int):
+    """The reference algorithm (oracle port: same tile ops, same DAG/priorities, 1 BLAS thread per tile
+    task, `threads` pool workers) on the host cores. Returns (GFLOP/s best-of-steps average, residual)."""
+    a = O.set_random_hermitian_positive_definite(n, nb, np.float64)
+    times = []
+    res = None
+    for i in range(warmup + steps):
+        w = a.copy(order="F")
+        t0 = time.perf_counter()
+        info = O.cholesky_local("L", w, nb, threads)
+        dt = time.perf_counter() - t0
+        assert info == 0
+        if i >= warmup:
+            times.append(dt)
+        if i == warmup + steps - 1 and n <= 8192:
+            res = O.residual("L", a, w)
+    return n ** 3 / 3 / (sum(times) / len(times)) / 1e9, sum(times) / len(times), res
+
+
+def pick_cpu_sample(O, nb: int, threads: int, budget_s: float, n_max: int) -> int:
+    """Largest N (multiple of nb, <= n_max) whose factorization is expected to stay within budget_s."""
+    n0 = max(nb * 4, 2048)
+    g, _, _ = cpu_reference_run(O, n0, nb, threads, 1, 1)
+    n = int((budget_s * g * 1e9 * 3) ** (1 / 3))
+    n = max(n0, min(n_max, n // nb * nb))
+    log(f"[cpu] probe N={n0}: {g:.1f} GFLOP/s on {threads} threads -> sample N={n}")
+    return n
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O = ge.load_oracle()
+    O.build()
+    threads = O.lib().oracle_hardware_threads()
+    # bounded sample: one step <= ~12 s so that warmup + steps finishes in minutes
+    n = args.cpu_sample_n or pick_cpu_sample(O, args.nb, threads, 12.0, args.n)
+    gf, sec, res = cpu_reference_run(O, n, args.nb, threads, args.steps, args.warmup)
+    sample = f"N={n} nb={args.nb} fp64, same generator, oracle port of impl.h:150-189 over OpenBLAS, {threads} pool threads x 1 BLAS thread"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"fp64 POTRF N={args.n} nb={args.nb} (CPU arm measured on the bounded sample N={n})",
+                   "sample": sample},
+        "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample,
+                         "blas": O.lib().oracle_blas_config().decode(), "residual": res},
+        "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def residual_check_torch(torch, d_ref, d_fac, n: int, blk: int = 4096):
+    """Checker (not product code): the miniapp's max|A - L L^T| / max|A| over the lower triangle
+    (miniapp_cholesky.cpp:408-446), evaluated block column by block column with torch fp64 matmul.
+    d_ref / d_fac are (n, n) torch views of column-major storage, i.e. indexed [col, row]."""
+    max_a = 0.0
+    max_d = 0.0
+    # In the [col,row] view X[j, i] = A(i, j); the lower triangle of A is the upper triangle of X.
+    Lt = torch.triu(d_fac)  # Lt[j, i] = L(i, j) for i >= j
+    for j0 in range(0, n, blk):
+        j1 = min(n, j0 + blk)
+        # (L L^T)(i, j) for j in block, i >= j0:  sum_k L(i,k) L(j,k) -> Lt[:, i]^T Lt[:, j]
+        prod = Lt[:j1, j0:j1].T @ Lt[:j1, j0:]  # [j, i], k < j1 suffices because L(j,k)=0 for k>j
+        a_blk = d_ref[j0:j1, j0:]
+        diff = torch.triu(a_blk - prod)  # keep i >= j (i index offset j0 on both axes)
+        max_d = max(max_d, diff.abs().max().item())
+        max_a = max(max_a, torch.triu(a_blk).abs().max().item())
+        del prod, diff
+    return max_d / max_a
+
+
+def triangle_bytes(n: int, nb: int, P: int, Q: int, vr: int, vc: int, itemsize: int) -> int:
+    nt = -(-n // nb)
+    total = 0
+    for gj in range(vc, nt, Q):
+        width = min(nb, n - gj * nb)
+        rows = sum(min(nb, n - gi * nb) for gi in range(vr, nt, P) if gi >= gj)
+        total += rows * width * itemsize
+    return total
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}: launch with torchrun --nproc-per-node {args.gpus}")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    os.environ["DLAF_B200_DEVICE"] = str(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = ge.load_package()
+    pkg.lib()  # fails loudly if the CUDA library has not been built (no fallback)
+    pkg.initialize()
+    P, Q = (args.grid_rows, args.grid_cols) if args.grid_rows and args.grid_cols else GRIDS.get(world, (1, world))
+    assert P * Q == world, f"grid {P}x{Q} does not match {world} ranks"
+    comm = pkg.comm_create_from_torch() if world > 1 else None
+    ctx = pkg.create_grid(comm, P, Q, "C")  # ColumnMajor like the miniapp (miniapp_cholesky.cpp:113)
+    _, _, myrow, mycol = pkg.grid_info(ctx)
+    n, nb = args.n, args.nb
+    desc0 = pkg.descriptor(n, nb, 1)
+    lr, lc = pkg.local_shape(ctx, desc0)
+    ld = lr
+    dtype = np.float64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- synthetic input: the miniapp's generator, into pinned host memory (column-major lr x lc)
+    t0 = time.perf_counter()
+    h_ref_t = torch.empty((lc, lr), dtype=torch.float64, pin_memory=True)
+    h_ref = h_ref_t.numpy().T  # (lr, lc) Fortran-ordered view
+    pkg.set_random_hermitian_positive_definite(ctx, h_ref, n, nb)
+    log(f"[bench] rank {rank}: generated local {lr}x{lc} in {time.perf_counter() - t0:.1f}s")
+    d_ref = h_ref_t.cuda()
+    d_work = torch.empty_like(d_ref)
+    stream = torch.cuda.current_stream()
+    pkg.set_profiling(ctx, True)
+    flops = pkg.total_ops(dtype, n)
+
+    # ---- device-resident steps (the miniapp's timed region)
+    W, K = args.warmup, args.steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    prof_ms = prof_fl = 0.0
+    prof_n = 0
+    launches = 0
+    for i in range(W):
+        d_work.copy_(d_ref)
+        barrier()
+        pkg.cholesky_factorization_device(ctx, "L", d_work.data_ptr(), dtype, n, nb, ld, stream.cuda_stream)
+        assert pkg.wait(ctx, stream.cuda_stream) == 0
+    sampler = ClockSampler(local_rank)
+    barrier()
+    wall0 = time.perf_counter()
+    with sampler:
+        for i in range(K):
+            d_work.copy_(d_ref)  # restore the input (not part of the step); matrix >> L2, so every step starts cold
+            barrier()
+            ev[i][0].record(stream)
+            pkg.cholesky_factorization_device(ctx, "L", d_work.data_ptr(), dtype, n, nb, ld, stream.cuda_stream)
+            ev[i][1].record(stream)
+            info = pkg.wait(ctx, stream.cuda_stream)
+            assert info == 0, f"info {info}"
+            ms, fl, cnt = pkg.read_profile(ctx)
+            prof_ms += ms
+            prof_fl += fl
+            prof_n += cnt
+            launches += pkg.last_launch_count(ctx)
+        barrier()
+    wall = time.perf_counter() - wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = allmax(sum(step_ms))
+    ms_per_step = total_ms / K
+    value = flops / (ms_per_step * 1e-3) / 1e9
+    clocks = sampler.summary()
+
+    # ---- correctness of the timed result (checker)
+    residual = None
+    if not args.no_check and world == 1:
+        try:
+            residual = residual_check_torch(torch, d_ref.view(n, n), d_work.view(n, n), n)
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] residual check skipped: {e}")
+
+    # ---- roofline of the dominant kernel (bulk trailing update, DMMA GEMM)
+    peak = pkg.measure_fp64_tensor_peak_tflops()
+    achieved = (prof_fl / (prof_ms * 1e-3) / 1e12) if prof_ms > 0 else None
+    roofline = {
+        "kernel": "gemm_nt_f64_kernel (bulk trailing update, stream L)", "bound": "tensor",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+        "traffic": None,
+        "peak_source": "measured now on this GPU: DMMA.8x8x4 issue-rate microbenchmark (dlaf_b200_measure_fp64_tensor_peak_tflops); "
+                       "MEASURED_PEAKS.json holds no fp64 figure (bf16 cuBLAS + HBM copy only); nominal B200 fp64 = 40 TFLOP/s",
+        "launches_timed": prof_n, "kernel_ms_per_step": prof_ms / K if K else None,
+        "kernel_share_of_step": (prof_ms / K) / ms_per_step if K else None,
+        "whole_potrf_frac_of_peak": value / 1e3 / (peak * world),
+    }
+    del d_work
+
+    # ---- end to end through the reference-facing C ABI with HOST buffers (H2D + D2H inside)
+    E = args.e2e_steps if args.e2e_steps >= 0 else min(K, 2)
+    e2e = None
+    if E > 0:
+        h_work_t = torch.empty((lc, lr), dtype=torch.float64, pin_memory=True)
+        h_work = h_work_t.numpy().T
+        times = []
+        for i in range(1 + E):
+            h_work_t.copy_(h_ref_t)
+            barrier()
+            t0 = time.perf_counter()
+            info = pkg.cholesky_factorization(ctx, "L", h_work, nb, n=n)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            assert info == 0
+            if i >= 1:
+                times.append(dt)
+        e2e_s = allmax(sum(times) / len(times))
+        tb = triangle_bytes(n, nb, P, Q, myrow, mycol, 8)
+        e2e = {"value": flops / e2e_s / 1e9, "unit": "GFLOP/s", "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": tb, "d2h_bytes_per_step": tb, "steps": E,
+               "api": "dlaf_cholesky_factorization_d (pinned host local matrix, referenced triangle only)"}
+        if not args.no_check and world == 1 and n <= 8192:
+            O = ge.load_oracle()
+            e2e["residual"] = O.residual("L", np.asfortranarray(h_ref), np.asfortranarray(h_work))
+
+    # ---- CPU baseline: the reference algorithm on this box's host cores, bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        O = ge.load_oracle()
+        O.build()
+        threads = O.lib().oracle_hardware_threads()
+        ns = args.cpu_sample_n or pick_cpu_sample(O, nb, threads, 15.0, n)
+        gf, sec, res = cpu_reference_run(O, ns, nb, threads, 1, 0)
+        cpu = {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": "port",
+               "sample": f"one factorization of N={ns} nb={nb} fp64 (same generator), {sec:.1f} s; oracle port of "
+                         f"cholesky/impl.h:150-189 over OpenBLAS, {threads} pool threads x 1 BLAS thread per tile op",
+               "residual": res}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"fp64 POTRF N={n} nb={nb} uplo=L, grid {P}x{Q} (ColumnMajor), device-resident, in place",
+                       "input": "set_random_hermitian_positive_definite (miniapp generator), restored before every step",
+                       "l2": "matrix (%.1f GB per GPU) is larger than L2; every step starts from a fresh copy" % (lr * lc * 8 / 1e9),
+                       "timing": "CUDA events on the launching stream per step, summed over K steps, max over ranks",
+                       "wall_s_incl_restore": wall},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "residual_max_diff_over_max_a": residual,
+            "residual_gate_eps_n": float(np.finfo(np.float64).eps * n),
+            "step_ms": step_ms,
+        }
+        print(json.dumps(line), flush=True)
+    pkg.free_grid(ctx)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)

@@ -26,13 +26,14 @@ TYPES = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128
 C_API_SYMBOLS = [
     "dlaf_initialize", "dlaf_finalize",
     "dlaf_create_grid", "dlaf_free_grid", "dlaf_free_all_grids", "grid_ordering",
-    "dlaf_b200_get_unique_id", "dlaf_b200_comm_create", "dlaf_b200_comm_destroy",
+    "dlaf_b200_get_unique_id", "dlaf_b200_comm_create", "dlaf_b200_comm_create_local", "dlaf_b200_comm_destroy",
     "make_dlaf_descriptor",
     *[f"dlaf_cholesky_factorization_{t}" for t in "sdcz"],
     *[f"dlaf_p{t}potrf" for t in "sdcz"],
     *[f"dlaf_b200_cholesky_factorization_device_{t}" for t in "sdcz"],
     *[f"dlaf_b200_set_random_hermitian_positive_definite_{t}" for t in "sdcz"],
     "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info",
+    "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
 ]
 
@@ -105,6 +106,8 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_get_unique_id.restype = None
     L.dlaf_b200_comm_create.argtypes = [vp, ci, ci]
     L.dlaf_b200_comm_create.restype = vp
+    L.dlaf_b200_comm_create_local.argtypes = [ci, ci]
+    L.dlaf_b200_comm_create_local.restype = vp
     L.dlaf_b200_comm_destroy.argtypes = [vp]
     L.dlaf_b200_comm_destroy.restype = None
     L.make_dlaf_descriptor.argtypes = [ci, ci, ci, ci, ctypes.POINTER(ci)]
@@ -128,6 +131,11 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_wait.restype = ci
     L.dlaf_b200_last_launch_count.argtypes = [ci]
     L.dlaf_b200_last_launch_count.restype = ctypes.c_long
+    L.dlaf_b200_set_profiling.argtypes = [ci, ci]
+    L.dlaf_b200_set_profiling.restype = None
+    L.dlaf_b200_read_profile.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    L.dlaf_b200_read_profile.restype = None
+    L.dlaf_b200_measure_fp64_tensor_peak_tflops.restype = ctypes.c_double
     L.dlaf_b200_grid_info.argtypes = [ci, ctypes.POINTER(ci)]
     L.dlaf_b200_grid_info.restype = None
     L.dlaf_b200_local_rows.argtypes = [ci, DLAF_descriptor]
@@ -165,6 +173,11 @@ def get_unique_id() -> bytes:
 
 def comm_create(unique_id: bytes, rank: int, nranks: int):
     return lib().dlaf_b200_comm_create(ctypes.c_char_p(unique_id), rank, nranks)
+
+
+def comm_create_local(rank: int, nranks: int):
+    """Geometry-only communicator (CPU tests of the N>1 host logic; cannot factorise)."""
+    return lib().dlaf_b200_comm_create_local(rank, nranks)
 
 
 def comm_create_from_torch():
@@ -242,6 +255,21 @@ def wait(ctx: int, stream: int = 0) -> int:
 
 def last_launch_count(ctx: int) -> int:
     return lib().dlaf_b200_last_launch_count(ctx)
+
+
+def set_profiling(ctx: int, enable: bool) -> None:
+    lib().dlaf_b200_set_profiling(ctx, 1 if enable else 0)
+
+
+def read_profile(ctx: int):
+    """(sum of bulk-update launch durations [ms], their algorithmic flops, number of launches)."""
+    out = (ctypes.c_double * 3)()
+    lib().dlaf_b200_read_profile(ctx, out)
+    return out[0], out[1], int(out[2])
+
+
+def measure_fp64_tensor_peak_tflops() -> float:
+    return lib().dlaf_b200_measure_fp64_tensor_peak_tflops()
 
 
 def set_random_hermitian_positive_definite(ctx: int, a: np.ndarray, n: int, nb: int, isrc: int = 0,

@@ -38,6 +38,8 @@ struct EngineSlotBase {
   virtual ~EngineSlotBase() = default;
   virtual int info(cudaStream_t s) = 0;
   virtual long launches() const = 0;
+  virtual void set_profiling(bool on) = 0;
+  virtual void read_profile(double out[3]) = 0;
 };
 
 template <class D>
@@ -49,6 +51,15 @@ struct EngineSlot : EngineSlotBase {
   ~EngineSlot() override { cudaFree(stage); }
   int info(cudaStream_t s) override { return eng ? eng->info(s) : 0; }
   long launches() const override { return eng ? eng->launches() : 0; }
+  void set_profiling(bool on) override {
+    if (eng)
+      eng->set_profiling(on);
+  }
+  void read_profile(double out[3]) override {
+    out[0] = out[1] = out[2] = 0;
+    if (eng)
+      eng->read_profile(out);
+  }
   D* ensure_stage(size_t elems) {
     if (elems > stage_elems) {
       cudaFree(stage);
@@ -63,6 +74,7 @@ struct GridCtx {
   std::unique_ptr<CommGrid> grid;
   std::unique_ptr<EngineSlotBase> slot[4];  // s, d, c, z
   int last_type = -1;
+  bool profiling = false;
   cudaStream_t stream = nullptr;  // stream of the synchronous host API
   int* d_red = nullptr;           // info reduction buffer
   ~GridCtx() {
@@ -235,6 +247,7 @@ EngineSlot<devtype_t<T>>& get_engine(GridCtx& c, const DLAF_descriptor& d, const
     }
     slot.key = key;
   }
+  slot.eng->set_profiling(c.profiling);
   c.last_type = ti;
   return slot;
 }
@@ -295,6 +308,8 @@ int cholesky_host(int ctx, char uplo, T* a, const DLAF_descriptor& desc) {
     return 0;
   const bool upper = is_upper(uplo);
   const UserGeom u = user_geometry(*c.grid, desc);
+  DLAF_B200_ASSERT(c.grid->P * c.grid->Q == 1 || c.grid->row_comm || c.grid->col_comm,
+                   "this grid was built on a geometry-only communicator");
   DLAF_B200_ASSERT(desc.ld >= std::max<long>(1, u.lrows), "leading dimension smaller than local rows");
   auto& slot = get_engine<T>(c, desc, u, upper);
   PotrfEngine<D>& eng = *slot.eng;
@@ -423,6 +438,13 @@ struct dlaf_b200_comm* dlaf_b200_comm_create(const void* id128, int rank, int nr
   return comm_create(id128, rank, nranks);
 }
 
+struct dlaf_b200_comm* dlaf_b200_comm_create_local(int rank, int nranks) noexcept {
+  Comm* c = new Comm;
+  c->rank = rank;
+  c->size = nranks;
+  return c;
+}
+
 void dlaf_b200_comm_destroy(struct dlaf_b200_comm* comm) noexcept {
   comm_destroy(comm);
 }
@@ -497,6 +519,21 @@ long dlaf_b200_last_launch_count(int ctx) noexcept {
   if (c.last_type < 0 || !c.slot[c.last_type])
     return 0;
   return c.slot[c.last_type]->launches();
+}
+
+void dlaf_b200_set_profiling(int ctx, int enable) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  c.profiling = enable != 0;
+  for (auto& s : c.slot)
+    if (s)
+      s->set_profiling(c.profiling);
+}
+
+void dlaf_b200_read_profile(int ctx, double out[3]) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  out[0] = out[1] = out[2] = 0;
+  if (c.last_type >= 0 && c.slot[c.last_type])
+    c.slot[c.last_type]->read_profile(out);
 }
 
 void dlaf_b200_grid_info(int ctx, int out[4]) noexcept {

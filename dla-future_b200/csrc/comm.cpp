@@ -46,6 +46,8 @@ CommGrid::CommGrid(Comm* world, int P_, int Q_, char order) : P(P_), Q(Q_) {
   }
   if (P * Q == 1)
     return;  // a 1x1 grid never communicates
+  if (world->nccl == nullptr)
+    return;  // geometry-only communicator (dlaf_b200_comm_create_local): no collectives possible
   // ncclCommSplit is collective over the parent: left-out ranks pass NCCL_SPLIT_NOCOLOR.
   DLAF_NCCL_CHECK(ncclCommSplit(world->nccl, in_grid ? row : NCCL_SPLIT_NOCOLOR, col, &row_comm, nullptr));
   DLAF_NCCL_CHECK(ncclCommSplit(world->nccl, in_grid ? col : NCCL_SPLIT_NOCOLOR, row, &col_comm, nullptr));

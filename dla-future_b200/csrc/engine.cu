@@ -71,6 +71,8 @@ PotrfEngine<T>::~PotrfEngine() {
     cudaEventDestroy(evB_[i]);
   }
   cudaEventDestroy(ev_start_);
+  for (auto e : prof_ev_)
+    cudaEventDestroy(e);
   cudaFree(own_slab_);
   cudaFree(d_info_);
   cudaFreeHost(h_info_);
@@ -400,12 +402,44 @@ void PotrfEngine<T>::update(int k, bool lookahead, cudaStream_t st) {
     }
     a.ldb = nbp_;
   }
+  if (profiling_ && !lookahead) {
+    // algorithmic flops of this launch: 2 nbp^3 per off-diagonal tile, nbp^3 per diagonal tile
+    // (herk), counted on global tile indices; complex: x4 (6 mul + 2 add per complex mac = 8 flop)
+    double tiles = 0;
+    for (int lj = cj0; lj < ltc_; ++lj) {
+      const long gj = static_cast<long>(lj) * Q + geo_.pcol;
+      for (int li = ri0; li < ltr_; ++li) {
+        const long gi = static_cast<long>(li) * P + geo_.prow;
+        if (gi > gj)
+          tiles += 2.0;
+        else if (gi == gj)
+          tiles += 1.0;
+      }
+    }
+    const double cplx = (sizeof(T) == 2 * sizeof(base_t<T>)) ? 4.0 : 1.0;
+    last_update_flops_ = tiles * cplx * static_cast<double>(nbp_) * nbp_ * nbp_;
+  }
   gemm(a, st);
+}
+
+template <class T>
+void PotrfEngine<T>::read_profile(double out[3]) {
+  out[0] = out[1] = out[2] = 0.0;
+  for (size_t i = 0; i < prof_used_; ++i) {
+    if (prof_flops_[i] < 0)
+      continue;  // nothing was launched for this step
+    float ms = 0.f;
+    DLAF_CUDA_CHECK(cudaEventElapsedTime(&ms, prof_ev_[2 * i], prof_ev_[2 * i + 1]));
+    out[0] += ms;
+    out[1] += prof_flops_[i];
+    out[2] += 1.0;
+  }
 }
 
 template <class T>
 void PotrfEngine<T>::factorize(cudaStream_t s) {
   launches_ = 0;
+  prof_used_ = 0;
   if (nt_ == 0)
     return;
   if (!external_)
@@ -419,7 +453,25 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   for (int k = 0; k < nt_ - 1; ++k) {
     // bulk of U_k on the low-priority stream
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sL_, evP_[k % 2], 0));
-    update(k, false, sL_);
+    if (profiling_) {
+      if (prof_ev_.size() < 2 * (prof_used_ + 1)) {
+        cudaEvent_t a, b;
+        DLAF_CUDA_CHECK(cudaEventCreate(&a));
+        DLAF_CUDA_CHECK(cudaEventCreate(&b));
+        prof_ev_.push_back(a);
+        prof_ev_.push_back(b);
+        prof_flops_.push_back(0.0);
+      }
+      const long before = launches_;
+      DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_], sL_));
+      update(k, false, sL_);
+      DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_ + 1], sL_));
+      prof_flops_[prof_used_] = (launches_ > before) ? last_update_flops_ : -1.0;
+      ++prof_used_;
+    }
+    else {
+      update(k, false, sL_);
+    }
     DLAF_CUDA_CHECK(cudaEventRecord(evB_[k % 2], sL_));
     // critical path on the high-priority stream: U_k(k+1), then P_{k+1}
     if (k >= 1)

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <nccl.h>
 
+#include <vector>
+
 #include "gemm_args.h"
 #include "layout.cuh"
 #include "potrf_tile.cuh"
@@ -77,6 +79,12 @@ public:
 
   long launches() const { return launches_; }  // kernels launched by the last factorize()
 
+  // Per-launch timing of the dominant kernel (the bulk trailing update on stream L) with CUDA events on
+  // its own stream: enable before factorize(), read after the stream has been synchronised.
+  void set_profiling(bool on) { profiling_ = on; }
+  // out = {sum of launch durations [ms], algorithmic flops of those launches, number of launches}
+  void read_profile(double out[3]);
+
 private:
   void panel_step(int k);
   void update(int k, bool lookahead, cudaStream_t st);
@@ -107,6 +115,11 @@ private:
   int* d_info_ = nullptr;
   int* h_info_ = nullptr;
   long launches_ = 0;
+  bool profiling_ = false;
+  std::vector<cudaEvent_t> prof_ev_;  // pairs (begin, end)
+  std::vector<double> prof_flops_;
+  size_t prof_used_ = 0;
+  double last_update_flops_ = 0.0;
 };
 
 }  // namespace dlaf_b200

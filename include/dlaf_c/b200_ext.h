@@ -23,6 +23,14 @@ DLAF_EXTERN_C int dlaf_b200_wait(int ctx, void* cuda_stream) DLAF_NOEXCEPT;
 /* Number of this library's kernel launches issued by the last factorization on ctx. */
 DLAF_EXTERN_C long dlaf_b200_last_launch_count(int ctx) DLAF_NOEXCEPT;
 
+/* Measurement hooks (bench.py): per-launch CUDA-event timing of the dominant kernel (bulk trailing
+ * update) on its own stream. read: out = {sum of durations [ms], algorithmic flops, launches} of the last
+ * factorization (call after dlaf_b200_wait). */
+DLAF_EXTERN_C void dlaf_b200_set_profiling(int ctx, int enable) DLAF_NOEXCEPT;
+DLAF_EXTERN_C void dlaf_b200_read_profile(int ctx, double out[3]) DLAF_NOEXCEPT;
+/* fp64 tensor-pipe (DMMA.8x8x4) issue-rate peak of the current device, TFLOP/s, measured now. */
+DLAF_EXTERN_C double dlaf_b200_measure_fp64_tensor_peak_tflops(void) DLAF_NOEXCEPT;
+
 /* Fill this rank's HOST local part with the miniapp's random Hermitian positive definite matrix. */
 DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_s(int ctx, float* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
 DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_d(int ctx, double* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;

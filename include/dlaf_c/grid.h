@@ -23,6 +23,9 @@ typedef struct dlaf_b200_comm* DLAF_Comm; /* NULL is valid for a 1x1 grid */
 DLAF_EXTERN_C void dlaf_b200_get_unique_id(void* id128) DLAF_NOEXCEPT;
 DLAF_EXTERN_C struct dlaf_b200_comm* dlaf_b200_comm_create(const void* id128, int rank,
                                                             int nranks) DLAF_NOEXCEPT;
+/* Geometry-only communicator (no NCCL object, no GPU needed): grids built on it answer layout queries
+ * (local sizes, coordinates, input generator) but abort on any factorization. */
+DLAF_EXTERN_C struct dlaf_b200_comm* dlaf_b200_comm_create_local(int rank, int nranks) DLAF_NOEXCEPT;
 DLAF_EXTERN_C void dlaf_b200_comm_destroy(struct dlaf_b200_comm* comm) DLAF_NOEXCEPT;
 
 /* Returns a context (counting down from INT_MAX like src/c_api/grid.cpp:28-40). order 'R' or 'C'. */

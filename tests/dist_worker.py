@@ -1,0 +1,137 @@
+"""Worker for the multi-process tests (one process per rank).
+
+  mode cpu : gloo, no GPU — host logic of the N>1 path: grid coordinates, local sizes and the
+             distribution-independent input generator, assembled across ranks and compared with the oracle.
+  mode gpu : nccl, one GPU per rank — distributed POTRF through the C ABI on a P x Q grid (with a non-zero
+             source rank like test/unit/factorization/test_cholesky.cpp:85) against the oracle's factor.
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+
+def coords(rank, P, Q, order):
+    return (rank % P, rank // P) if order == "C" else (rank // Q, rank % Q)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", required=True, choices=["cpu", "gpu"])
+    ap.add_argument("--grid", default="2x1")
+    ap.add_argument("--order", default="R")
+    ap.add_argument("--big", action="store_true")
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+
+    P, Q = (int(x) for x in a.grid.split("x"))
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    pkg = ge.load_package()
+    O = ge.load_oracle()
+    if a.mode == "cpu":
+        dist.init_process_group("gloo")
+        comm = pkg.comm_create_local(rank, world)
+    else:
+        lr = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        pkg.initialize()
+        comm = pkg.comm_create_from_torch()
+    ctx = pkg.create_grid(comm, P, Q, a.order)
+    gP, gQ, myrow, mycol = pkg.grid_info(ctx)
+    assert (gP, gQ) == (P, Q)
+    if rank < P * Q:
+        assert (myrow, mycol) == coords(rank, P, Q, a.order), (rank, myrow, mycol)
+
+    src = (max(0, P - 1), min(1, Q - 1))  # test_cholesky.cpp:85
+    failures = []
+    if a.mode == "cpu":
+        cases = [(37, 8, "d"), (64, 16, "z"), (21, 5, "s")]
+        for n, nb, t in cases:
+            dt = pkg.TYPES[t]
+            for s in [(0, 0), src]:
+                if rank >= P * Q:
+                    continue
+                d = pkg.descriptor(n, nb, 1, s[0], s[1])
+                lrows, lcols = pkg.local_shape(ctx, d)
+                assert lrows == O.local_size(n, nb, P, myrow, s[0]) and lcols == O.local_size(n, nb, Q, mycol, s[1])
+                loc = np.zeros((lrows, lcols), dtype=dt, order="F")
+                if lrows and lcols:
+                    pkg.set_random_hermitian_positive_definite(ctx, loc, n, nb, s[0], s[1])
+                ref = O.scatter_block_cyclic(O.set_random_hermitian_positive_definite(n, nb, dt), nb, (P, Q), s)
+                if not np.array_equal(loc, ref[(myrow, mycol)]):
+                    failures.append(("generator", n, nb, t, s))
+        # the 128-byte bootstrap payload travels over torch.distributed unchanged
+        obj = [os.urandom(128) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, obj[0])
+        assert all(g == gathered[0] and len(g) == 128 for g in gathered)
+    else:
+        cases = [(0, 2), (5, 8), (34, 34), (4, 3), (16, 10), (34, 13), (32, 5)]  # test_cholesky.cpp:54-58
+        sized = [(m, mb, t) for (m, mb) in cases for t in "sdcz"]
+        sized += [(1000, 128, "d"), (1536, 256, "d"), (700, 64, "z"), (1100, 100, "s"), (640, 64, "c")]
+        if a.big:
+            sized += [(8192, 512, "d"), (6144, 512, "z")]
+        for n, nb, t in sized:
+            dt = pkg.TYPES[t]
+            for uplo in "LU":
+                for s in ([(0, 0), src] if n < 2000 else [(0, 0)]):
+                    if n <= 64:
+                        A, expect = O.cholesky_setters(uplo, n, dt)
+                    else:
+                        A = O.set_random_hermitian_positive_definite(n, nb, dt)
+                        expect = A.copy(order="F")
+                        assert O.cholesky_local(uplo, expect, nb, 8) == 0
+                    if rank < P * Q:
+                        loc = np.asfortranarray(O.scatter_block_cyclic(A, nb, (P, Q), s)[(myrow, mycol)])
+                        exp_loc = O.scatter_block_cyclic(expect, nb, (P, Q), s)[(myrow, mycol)]
+                        orig = loc.copy(order="F")
+                    else:
+                        loc = np.zeros((1, 1), dtype=dt, order="F")
+                    info = pkg.cholesky_factorization(ctx, uplo, loc, nb, n=n, isrc=s[0], jsrc=s[1])
+                    if rank >= P * Q:
+                        continue
+                    tol = O.cholesky_tolerance(n, dt)
+                    if n <= 64:
+                        ok, _, msg = O.check_near(exp_loc, loc, tol, tol)
+                    else:
+                        # compare only the referenced triangle (global indices), the rest must be untouched
+                        gi = np.concatenate([np.arange(g * nb, min(n, (g + 1) * nb)) for g in range(-(-n // nb)) if O.rank_global_tile(g, P, s[0]) == myrow] or [np.zeros(0, int)])
+                        gj = np.concatenate([np.arange(g * nb, min(n, (g + 1) * nb)) for g in range(-(-n // nb)) if O.rank_global_tile(g, Q, s[1]) == mycol] or [np.zeros(0, int)])
+                        mask = (gi[:, None] >= gj[None, :]) if uplo == "L" else (gi[:, None] <= gj[None, :])
+                        ok, _, msg = O.check_near(np.where(mask, exp_loc, 0), np.where(mask, loc, 0), tol, tol)
+                        if ok and not np.array_equal(np.where(mask, 0, loc), np.where(mask, 0, orig)):
+                            ok, msg = False, "unreferenced triangle modified"
+                    if info != 0 or not ok:
+                        failures.append((n, nb, t, uplo, s, info, msg))
+        # non-SPD: every rank must report the same LAPACK info
+        n, nb = 300, 64
+        B = np.eye(n, order="F") * 4.0
+        B[200, 200] = -1.0
+        if rank < P * Q:
+            loc = np.asfortranarray(O.scatter_block_cyclic(B, nb, (P, Q), (0, 0))[(myrow, mycol)])
+        else:
+            loc = np.zeros((1, 1), order="F")
+        info = pkg.cholesky_factorization(ctx, "L", loc, nb, n=n)
+        if rank < P * Q and info != 201:
+            failures.append(("info", info))
+    flag = torch.tensor([len(failures)], dtype=torch.int64, device="cuda" if a.mode == "gpu" else "cpu")
+    dist.all_reduce(flag)
+    if failures:
+        print(f"rank {rank} FAILURES: {failures[:5]}", flush=True)
+    if rank == 0:
+        print(f"dist_worker mode={a.mode} grid={P}x{Q} order={a.order}: total failures {int(flag.item())}", flush=True)
+    pkg.free_grid(ctx)
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,8 +1,8 @@
 # Build of the B200 POTRF engine (sm_100a only), its C-ABI shared library and test tools.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Iinclude
-CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -Iinclude -I/usr/local/cuda/include
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo --extended-lambda -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas -Iinclude
+CXXFLAGS  := -O2 -std=c++17 -fPIC -Wall -Wno-unknown-pragmas -Iinclude -I/usr/local/cuda/include
 CSRC      := dla-future_b200/csrc
 LIBDIR    := dla-future_b200/lib
 LIB       := $(LIBDIR)/libdlaf_b200.so

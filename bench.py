@@ -134,7 +134,7 @@ def run_reference_arm(args):
         return
     O = ge.load_oracle()
     O.build()
-    threads = O.lib().oracle_hardware_threads()
+    threads = O.max_pool_threads()
     # bounded sample: one step <= ~12 s so that warmup + steps finishes in minutes
     n = args.cpu_sample_n or pick_cpu_sample(O, args.nb, threads, 12.0, args.n)
     gf, sec, res = cpu_reference_run(O, n, args.nb, threads, args.steps, args.warmup)
@@ -146,7 +146,8 @@ def run_reference_arm(args):
         "config": {"workload": f"fp64 POTRF N={args.n} nb={args.nb} (CPU arm measured on the bounded sample N={n})",
                    "sample": sample},
         "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": "port", "sample": sample,
-                         "blas": O.lib().oracle_blas_config().decode(), "residual": res},
+                         "blas": O.lib().oracle_blas_config().decode(), "residual": res,
+                         "host_hw_threads": O.lib().oracle_hardware_threads()},
         "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -323,18 +324,20 @@ def run_ours(args):
             O = ge.load_oracle()
             e2e["residual"] = O.residual("L", np.asfortranarray(h_ref), np.asfortranarray(h_work))
 
-    # ---- CPU baseline: the reference algorithm on this box's host cores, bounded sample
+    # ---- CPU baseline: the reference algorithm on this box's host cores, bounded sample. Runs in a child
+    # process (the reference arm of this script) so that a host BLAS problem cannot take the bench down.
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        O = ge.load_oracle()
-        O.build()
-        threads = O.lib().oracle_hardware_threads()
-        ns = args.cpu_sample_n or pick_cpu_sample(O, nb, threads, 15.0, n)
-        gf, sec, res = cpu_reference_run(O, ns, nb, threads, 1, 0)
-        cpu = {"value": gf, "unit": "GFLOP/s", "cores": threads, "kind": "port",
-               "sample": f"one factorization of N={ns} nb={nb} fp64 (same generator), {sec:.1f} s; oracle port of "
-                         f"cholesky/impl.h:150-189 over OpenBLAS, {threads} pool threads x 1 BLAS thread per tile op",
-               "residual": res}
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "0",
+               "--n", str(n), "--nb", str(nb)]
+        if args.cpu_sample_n:
+            cmd += ["--cpu-sample-n", str(args.cpu_sample_n)]
+        try:
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+            cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as e:  # pragma: no cover
+            cpu = {"value": None, "unit": "GFLOP/s", "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
 
     if rank == 0:
         line = {

@@ -5,11 +5,37 @@
 
 namespace dlaf_b200 {
 
+namespace {
+
+template <class Cfg>
+void launch_cfg(const GemmArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    DLAF_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_f64_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(a.M / Cfg::BM, a.N / Cfg::BN);
+  gemm_nt_f64_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+
+int sm_count() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+
+}  // namespace
+
 void launch_gemm_nt_f64(const GemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg128;
   if (a.M <= 0 || a.N <= 0)
     return;
-  DLAF_B200_ASSERT(a.M % Cfg::BM == 0 && a.N % Cfg::BN == 0 && a.K % Cfg::BK == 0 && a.K > 0,
+  DLAF_B200_ASSERT(a.M % 128 == 0 && a.N % 128 == 0 && a.K % 16 == 0 && a.K > 0,
                    "gemm shape must be a multiple of the CTA tile");
   DLAF_B200_ASSERT(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0,
                    "16-byte aligned operand columns");
@@ -18,16 +44,20 @@ void launch_gemm_nt_f64(const GemmArgs& a, cudaStream_t stream) {
                        (reinterpret_cast<uintptr_t>(a.C) & 15) == 0,
                    "16-byte aligned operands");
   DLAF_B200_ASSERT(a.a_ts % 2 == 0 && a.b_ts % 2 == 0, "16-byte aligned panel tiles");
-  static bool configured = false;
-  if (!configured) {
-    DLAF_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_f64_kernel<Cfg>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::SMEM_BYTES));
-    configured = true;
-  }
-  dim3 grid(a.M / Cfg::BM, a.N / Cfg::BN);
-  gemm_nt_f64_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
-  DLAF_CUDA_CHECK(cudaGetLastError());
+  // Tile choice: a problem that cannot fill the GPU with 128x128 tiles is latency-bound (it sits on
+  // the critical path of the factorization), so spread it over 2x / 4x more CTAs.
+  long ctas = static_cast<long>(a.M / 128) * (a.N / 128);
+  if (a.mask == kMaskLower && a.M == a.N)
+    ctas = ctas / 2 + a.M / 256;
+  const bool in_place = (static_cast<const void*>(a.A) == static_cast<const void*>(a.C));
+  DLAF_B200_ASSERT(!in_place || a.N == 128, "in-place product needs one CTA column");
+  if (ctas >= sm_count())
+    launch_cfg<GemmCfg128>(a, stream);
+  else if (in_place)
+    // C aliases A: one CTA must own all N columns of its rows (N == 128 == BN)
+    launch_cfg<GemmCfg64x128>(a, stream);
+  else
+    launch_cfg<GemmCfg64>(a, stream);
 }
 
 template <>

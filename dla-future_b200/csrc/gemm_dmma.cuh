@@ -47,9 +47,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 }  // namespace gemm_detail
 
-template <int BM_, int BN_, int BK_, int STAGES_>
+template <int BM_, int BN_, int BK_, int STAGES_, int MINB_ = 1>
 struct GemmCfg {
-  static constexpr int BM = BM_, BN = BN_, BK = BK_, STAGES = STAGES_;
+  static constexpr int BM = BM_, BN = BN_, BK = BK_, STAGES = STAGES_, MINB = MINB_;
   static constexpr int THREADS = 256;
   // +4 doubles of padding: the DMMA fragment read (k = lane&3, m = lane>>2) then hits 16 distinct
   // 8-byte banks per half-warp (row stride == 4 mod 16 doubles) -> conflict-free LDS.64.
@@ -64,7 +64,7 @@ struct GemmCfg {
 };
 
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_f64_kernel(const GemmArgs p) {
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(const GemmArgs p) {
   using namespace gemm_detail;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int FM = Cfg::FM, FN = Cfg::FN;
@@ -220,7 +220,12 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1) gemm_nt_f64_kernel(const Gemm
   }
 }
 
-using GemmCfg128 = GemmCfg<128, 128, 16, 4>;
+// Throughput configuration (bulk trailing update) and two latency configurations for the small
+// GEMMs on the critical path (in-tile steps, panel TRSM of the last steps): 2x / 4x more CTAs per
+// problem, two CTAs resident per SM.
+using GemmCfg128 = GemmCfg<128, 128, 16, 4, 1>;
+using GemmCfg64x128 = GemmCfg<64, 128, 16, 4, 2>;
+using GemmCfg64 = GemmCfg<64, 64, 16, 4, 2>;
 
 // Host launcher (defined in gemm_dmma.cu).
 void launch_gemm_nt_f64(const GemmArgs& args, cudaStream_t stream);

@@ -1,0 +1,304 @@
+// Register-resident blocked Cholesky + triangular inverse of one G x G diagonal block (G = 128 real,
+// 64 complex) by a single CTA of 256 threads — the per-thread phase functions. They are
+// __host__ __device__ so that tools/potrf_block_emu.cu can run the very same code for all 256 "threads"
+// on the CPU (there is no GPU in the build container).
+//
+// Data layout: the block S (lower: A -> L, strictly upper: X = inv(L)^H under construction, see
+// potrf_tile.cu for the rank-1 form of the rule) is spread over the register files: thread (ti, tj) of a
+// 16 x 16 grid owns the BS x BS sub-block rows ti*BS.., columns tj*BS.. (BS = G/16).
+// Per panel step J (BS columns at a time):
+//   A1  owners of block column J publish it to shared memory (k-major, padded per row block)
+//   A2  one thread per row: every thread re-derives the Cholesky of the BS x BS pivot block D in
+//       registers (redundantly — cheaper than a barrier per column), then solves its own panel row
+//       x <- x L_D^-H; the BS pivot rows instead receive L_D and X_D = inv(L_D)^H
+//   B   every thread applies the rank-BS update to its register block:
+//         S(r,s) -= sum_k P(r,k) conj(P(s,k))   for block columns right of J, rows r >= s or r < J*BS
+//       and the pivot block row gets the freshly created X entries  -(X_D-weighted combination).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+
+#include "types.h"
+
+namespace dlaf_b200 {
+namespace pblock {
+
+#define PB_HD __host__ __device__ __forceinline__
+
+PB_HD float re_of(float v) { return v; }
+PB_HD double re_of(double v) { return v; }
+PB_HD float re_of(float2 v) { return v.x; }
+PB_HD double re_of(double2 v) { return v.x; }
+
+PB_HD float scale_r(float v, float s) { return v * s; }
+PB_HD double scale_r(double v, double s) { return v * s; }
+PB_HD float2 scale_r(float2 v, float s) { return make_float2(v.x * s, v.y * s); }
+PB_HD double2 scale_r(double2 v, double s) { return make_double2(v.x * s, v.y * s); }
+
+// v - a * conj(b)
+PB_HD float sub_mul_conj(float v, float a, float b) { return fmaf(-a, b, v); }
+PB_HD double sub_mul_conj(double v, double a, double b) { return fma(-a, b, v); }
+PB_HD float2 sub_mul_conj(float2 v, float2 a, float2 b) {
+  return make_float2(fmaf(-a.y, b.y, fmaf(-a.x, b.x, v.x)), fmaf(a.x, b.y, fmaf(-a.y, b.x, v.y)));
+}
+PB_HD double2 sub_mul_conj(double2 v, double2 a, double2 b) {
+  return make_double2(fma(-a.y, b.y, fma(-a.x, b.x, v.x)), fma(a.x, b.y, fma(-a.y, b.x, v.y)));
+}
+// v - a * b
+PB_HD float sub_mul(float v, float a, float b) { return fmaf(-a, b, v); }
+PB_HD double sub_mul(double v, double a, double b) { return fma(-a, b, v); }
+PB_HD float2 sub_mul(float2 v, float2 a, float2 b) {
+  return make_float2(fmaf(a.y, b.y, fmaf(-a.x, b.x, v.x)), fmaf(-a.x, b.y, fmaf(-a.y, b.x, v.y)));
+}
+PB_HD double2 sub_mul(double2 v, double2 a, double2 b) {
+  return make_double2(fma(a.y, b.y, fma(-a.x, b.x, v.x)), fma(-a.x, b.y, fma(-a.y, b.x, v.y)));
+}
+
+PB_HD float fast_rsqrt(float a) {
+#ifdef __CUDA_ARCH__
+  float y = rsqrtf(a);
+  return fmaf(y * 0.5f, fmaf(-a * y, y, 1.0f), y);
+#else
+  return 1.0f / std::sqrt(a);
+#endif
+}
+PB_HD double fast_rsqrt(double a) {
+#ifdef __CUDA_ARCH__
+  double y = rsqrt(a);
+  return fma(y * 0.5, fma(-a * y, y, 1.0), y);
+#else
+  return 1.0 / std::sqrt(a);
+#endif
+}
+PB_HD float full_sqrt(float a) { return sqrtf(a); }
+PB_HD double full_sqrt(double a) { return sqrt(a); }
+
+template <class T, int PB_>
+struct Cfg {
+  static constexpr int PB = PB_;
+  static constexpr int NT = 16;        // thread grid edge
+  static constexpr int BS = PB / NT;   // register block edge = panel width
+  static constexpr int PAD = (16 / sizeof(T)) > 0 ? (16 / sizeof(T)) : 1;  // 16 bytes per row block
+  static constexpr int RS = BS + PAD;  // padded row-block stride: spreads the 16 row blocks over the banks
+  static constexpr int PROW = NT * RS;
+  static constexpr int PANEL_ELEMS = BS * PROW;
+  PB_HD static int poff(int r) { return (r / BS) * RS + (r % BS); }
+};
+
+template <class C, class T>
+PB_HD void load_block(T (&reg)[C::BS][C::BS], const T* Tm, long ldt, int ti, int tj) {
+#pragma unroll
+  for (int b = 0; b < C::BS; ++b)
+#pragma unroll
+    for (int a = 0; a < C::BS; ++a) {
+      const int r = ti * C::BS + a, s = tj * C::BS + b;
+      reg[a][b] = (r >= s) ? Tm[r + s * ldt] : make_real<T>(0);
+    }
+}
+
+// A1 (threads with tj == J)
+template <class C, class T>
+PB_HD void write_panel(const T (&reg)[C::BS][C::BS], T* panel, int ti) {
+#pragma unroll
+  for (int b = 0; b < C::BS; ++b)
+#pragma unroll
+    for (int a = 0; a < C::BS; ++a)
+      panel[b * C::PROW + C::poff(ti * C::BS + a)] = reg[a][b];
+}
+
+// A2 (row r = t % PB; only threads with `active` write). `sync` is called once, after every thread has
+// read the pivot block and its own row and before any row is written back (the pivot rows are part of
+// what the others read): __syncthreads() on the device, a no-op in the host emulation (which feeds
+// each thread a snapshot). Returns 0 or the 1-based in-block column where the pivot failed (identical
+// in every thread because the pivot block is factorised redundantly).
+template <class C, class T, class SyncF>
+PB_HD int factor_panel_row(T* panel, base_t<T>* dd, base_t<T>* dinv, int J, int t, bool active, SyncF sync) {
+  using R = base_t<T>;
+  constexpr int BS = C::BS;
+  T Dm[BS][BS];
+#pragma unroll
+  for (int b = 0; b < BS; ++b)
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+      Dm[a][b] = (a >= b) ? panel[b * C::PROW + C::poff(J * BS + a)] : make_real<T>(0);
+  const int r = t % C::PB, rb = r / BS, rr = r % BS;
+  T x[BS];
+#pragma unroll
+  for (int k = 0; k < BS; ++k)
+    x[k] = panel[k * C::PROW + C::poff(r)];
+  sync();
+  R invd[BS], dsq[BS];
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    const R ajj = re_of(Dm[j][j]);
+    if (!(ajj > R(0)))
+      return j + 1;
+    invd[j] = fast_rsqrt(ajj);
+    dsq[j] = ajj;  // sqrt taken later, only by the row that needs it
+#pragma unroll
+    for (int a = j + 1; a < BS; ++a)
+      Dm[a][j] = scale_r(Dm[a][j], invd[j]);
+#pragma unroll
+    for (int s = j + 1; s < BS; ++s)
+#pragma unroll
+      for (int a = s; a < BS; ++a)
+        Dm[a][s] = sub_mul_conj(Dm[a][s], Dm[a][j], Dm[s][j]);
+  }
+  if (!active)
+    return 0;
+  if (rb != J) {
+    // x <- x L_D^-H : Cholesky rows below the pivot block AND inverse rows above it obey the same rule
+#pragma unroll
+    for (int s = 0; s < BS; ++s) {
+      T v = x[s];
+#pragma unroll
+      for (int j = 0; j < s; ++j)
+        v = sub_mul_conj(v, x[j], Dm[s][j]);
+      x[s] = scale_r(v, invd[s]);
+    }
+  }
+  else {
+    // pivot row rr: [ L_D(rr, 0..rr-1) | diag | X_D(rr, s) = conj(M_D(s, rr)), s > rr ],  M_D = inv(L_D)
+    T m[BS];
+#pragma unroll
+    for (int s = 0; s < BS; ++s)
+      m[s] = make_real<T>(0);
+#pragma unroll
+    for (int c = 0; c < BS; ++c) {
+      if (c != rr)
+        continue;
+      m[c] = make_real<T>(invd[c]);
+#pragma unroll
+      for (int s = 0; s < BS; ++s) {
+        if (s <= c)
+          continue;
+        T v = make_real<T>(0);
+#pragma unroll
+        for (int j = 0; j < BS; ++j)
+          if (j >= c && j < s)
+            v = sub_mul(v, Dm[s][j], m[j]);
+        m[s] = scale_r(v, invd[s]);
+      }
+    }
+    // (static indices only: a run-time row index would push Dm into local memory)
+#pragma unroll
+    for (int s = 0; s < BS; ++s) {
+      if (s > rr)
+        x[s] = conj_val(m[s]);
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+        if (a == rr && s < a)
+          x[s] = Dm[a][s];
+    }
+#pragma unroll
+    for (int s = 0; s < BS; ++s)
+      if (s == rr) {
+        const R d = full_sqrt(dsq[s]);
+        x[s] = make_real<T>(d);
+        dd[r] = d;
+        dinv[r] = invd[s];
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < BS; ++k)
+    panel[k * C::PROW + C::poff(r)] = x[k];
+  return 0;
+}
+
+// B (all threads)
+template <class C, class T>
+PB_HD void update_block(T (&reg)[C::BS][C::BS], const T* panel, const base_t<T>* dinv, int J, int ti, int tj) {
+  using R = base_t<T>;
+  constexpr int BS = C::BS;
+  if (tj < J)
+    return;
+  if (tj == J) {  // take the final panel values back into the registers
+#pragma unroll
+    for (int b = 0; b < BS; ++b)
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+        reg[a][b] = panel[b * C::PROW + C::poff(ti * BS + a)];
+    return;
+  }
+  const bool full = (ti > tj) || (ti < J);
+  const bool diag = (ti == tj);
+  const bool piv = (ti == J);
+  if (!(full || diag || piv))
+    return;  // rows strictly between the pivot block and the column's own diagonal block: still zero
+  if (piv) {
+    R dv[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a) {
+      dv[a] = dinv[J * BS + a];
+#pragma unroll
+      for (int b = 0; b < BS; ++b)
+        reg[a][b] = make_real<T>(0);
+    }
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+      T rk[BS], ck[BS];
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+        rk[a] = panel[k * C::PROW + C::poff(ti * BS + a)];
+#pragma unroll
+      for (int b = 0; b < BS; ++b)
+        ck[b] = panel[k * C::PROW + C::poff(tj * BS + b)];
+#pragma unroll
+      for (int a = 0; a < BS; ++a) {
+        if (k < a)
+          continue;
+        const T coef = (k == a) ? make_real<T>(dv[a]) : rk[a];
+#pragma unroll
+        for (int b = 0; b < BS; ++b)
+          reg[a][b] = sub_mul_conj(reg[a][b], coef, ck[b]);
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < BS; ++k) {
+    T rk[BS], ck[BS];
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+      rk[a] = panel[k * C::PROW + C::poff(ti * BS + a)];
+#pragma unroll
+    for (int b = 0; b < BS; ++b)
+      ck[b] = panel[k * C::PROW + C::poff(tj * BS + b)];
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+#pragma unroll
+      for (int b = 0; b < BS; ++b)
+        if (!diag || a >= b)
+          reg[a][b] = sub_mul_conj(reg[a][b], rk[a], ck[b]);
+  }
+}
+
+// final store: L into the lower triangle of T (never touching the strictly upper part), inv(L) into W
+template <class C, class T>
+PB_HD void store_block(const T (&reg)[C::BS][C::BS], T* Tm, long ldt, T* W, long ldw, const base_t<T>* dd,
+                       const base_t<T>* dinv, int ti, int tj) {
+  constexpr int BS = C::BS;
+#pragma unroll
+  for (int b = 0; b < BS; ++b)
+#pragma unroll
+    for (int a = 0; a < BS; ++a) {
+      const int r = ti * BS + a, s = tj * BS + b;
+      if (r > s) {
+        Tm[r + s * ldt] = reg[a][b];
+        W[s + r * ldw] = make_real<T>(0);  // strictly upper part of W
+      }
+      else if (r == s) {
+        Tm[r + s * ldt] = make_real<T>(dd[r]);
+        W[r + s * ldw] = make_real<T>(dinv[r]);
+      }
+      else {
+        // r < s: this register holds X(r, s) = conj(inv(L)(s, r))
+        W[s + r * ldw] = conj_val(reg[a][b]);
+      }
+    }
+}
+
+}  // namespace pblock
+}  // namespace dlaf_b200

@@ -13,7 +13,11 @@
 // so one sweep with two barriers per column yields both L and inv(L).
 #include "potrf_tile.cuh"
 
+#include <cstdlib>
+#include <string>
+
 #include "common.h"
+#include "potrf_block.cuh"
 #include "types.h"
 
 namespace dlaf_b200 {
@@ -161,8 +165,70 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
   }
 }
 
+// ---- the blocked, register-resident kernel (potrf_block.cuh) -------------------------------------
+template <class T, int PB>
+__global__ void __launch_bounds__(kPotrfThreads, 1)
+    potrf_inv_blocked_kernel(T* __restrict__ Tm, long ldt, T* __restrict__ W, long ldw, int* info,
+                             int info_offset) {
+  using C = pblock::Cfg<T, PB>;
+  using R = base_t<T>;
+  constexpr int BS = C::BS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* panel = reinterpret_cast<T*>(smem_raw);
+  R* dd = reinterpret_cast<R*>(panel + C::PANEL_ELEMS);
+  R* dinv = dd + PB;
+  int* sfail = reinterpret_cast<int*>(dinv + PB);
+  const int tid = threadIdx.x, ti = tid % 16, tj = tid / 16;
+
+  T reg[BS][BS];
+  pblock::load_block<C, T>(reg, Tm, ldt, ti, tj);
+  if (tid == 0)
+    *sfail = 0;
+  int fail = 0;
+  for (int J = 0; J < 16; ++J) {
+    if (tj == J)
+      pblock::write_panel<C, T>(reg, panel, ti);
+    __syncthreads();
+    const int f = pblock::factor_panel_row<C, T>(panel, dd, dinv, J, tid, tid < PB, [] { __syncthreads(); });
+    if (f && tid == 0)
+      *sfail = J * BS + f;
+    __syncthreads();
+    fail = *sfail;
+    if (fail)
+      break;
+    pblock::update_block<C, T>(reg, panel, dinv, J, ti, tj);
+    __syncthreads();
+  }
+  if (fail) {
+    if (tid == 0)
+      atomicCAS(info, 0, info_offset + fail);
+    for (int idx = tid; idx < PB * PB; idx += kPotrfThreads)
+      W[(idx % PB) + (idx / PB) * ldw] = zero_of<T>();
+    return;
+  }
+  pblock::store_block<C, T>(reg, Tm, ldt, W, ldw, dd, dinv, ti, tj);
+}
+
+template <class T>
+void launch_blocked(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
+  constexpr int PB = Gran<T>::value;
+  using C = pblock::Cfg<T, PB>;
+  constexpr int smem = C::PANEL_ELEMS * sizeof(T) + 2 * PB * sizeof(base_t<T>) + 16;
+  potrf_inv_blocked_kernel<T, PB><<<1, kPotrfThreads, smem, stream>>>(t, ldt, w, ldw, info, info_offset);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+
 template <class T>
 void launch_impl(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
+  // DLAF_B200_POTRF_KERNEL=sweep selects the simple shared-memory sweep (kept for A/B measurements)
+  static const bool use_sweep = [] {
+    const char* e = std::getenv("DLAF_B200_POTRF_KERNEL");
+    return e && std::string(e) == "sweep";
+  }();
+  if (!use_sweep) {
+    launch_blocked<T>(t, ldt, w, ldw, info, info_offset, stream);
+    return;
+  }
   constexpr int PB = Gran<T>::value;
   constexpr int smem = (PB * (PB + 1)) * sizeof(T) + 2 * PB * sizeof(base_t<T>);
   static bool configured = false;

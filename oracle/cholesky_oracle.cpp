@@ -431,3 +431,9 @@ extern "C" const char* oracle_blas_config() {
 extern "C" int oracle_hardware_threads() {
   return static_cast<int>(std::thread::hardware_concurrency());
 }
+// Largest pool size the BLAS underneath tolerates: the scipy wheel's OpenBLAS is built with
+// MAX_THREADS=64 and aborts ("too many memory regions") when more threads call it concurrently.
+extern "C" int oracle_max_pool_threads() {
+  const int hw = static_cast<int>(std::thread::hardware_concurrency());
+  return hw < 1 ? 1 : (hw > 56 ? 56 : hw);
+}

@@ -51,7 +51,13 @@ def lib() -> ctypes.CDLL:
             f.restype = ctypes.c_double
         _LIB.oracle_blas_config.restype = ctypes.c_char_p
         _LIB.oracle_hardware_threads.restype = ctypes.c_int
+        _LIB.oracle_max_pool_threads.restype = ctypes.c_int
     return _LIB
+
+
+def max_pool_threads() -> int:
+    """Host threads the tiled CPU run may use (capped by what the wheel's OpenBLAS tolerates)."""
+    return lib().oracle_max_pool_threads()
 
 
 def type_char(dtype) -> str:

@@ -1,6 +1,8 @@
 // Host launcher for the fp64 DMMA GEMM (see gemm_dmma.cuh).
 #include "gemm_dmma.cuh"
 
+#include <cstdlib>
+
 #include "common.h"
 
 namespace dlaf_b200 {
@@ -32,6 +34,17 @@ int sm_count() {
 
 }  // namespace
 
+void launch_gemm_nt_f64_cfg(const GemmArgs& a, int cfg, cudaStream_t stream) {
+  switch (cfg) {
+    case 0: launch_cfg<GemmCfg128>(a, stream); break;
+    case 1: launch_cfg<GemmCfg64x128>(a, stream); break;
+    case 2: launch_cfg<GemmCfg64>(a, stream); break;
+    case 3: launch_cfg<GemmCfg128k32>(a, stream); break;
+    case 4: launch_cfg<GemmCfg128x64>(a, stream); break;
+    default: DLAF_B200_ASSERT(false, "unknown gemm configuration");
+  }
+}
+
 void launch_gemm_nt_f64(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0)
     return;
@@ -51,8 +64,12 @@ void launch_gemm_nt_f64(const GemmArgs& a, cudaStream_t stream) {
     ctas = ctas / 2 + a.M / 256;
   const bool in_place = (static_cast<const void*>(a.A) == static_cast<const void*>(a.C));
   DLAF_B200_ASSERT(!in_place || a.N == 128, "in-place product needs one CTA column");
+  static const int bulk_cfg = [] {
+    const char* e = std::getenv("DLAF_B200_GEMM_BULK_CFG");
+    return e ? std::atoi(e) : 1;  // 64x128, two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+  }();
   if (ctas >= sm_count())
-    launch_cfg<GemmCfg128>(a, stream);
+    launch_gemm_nt_f64_cfg(a, bulk_cfg, stream);
   else if (in_place)
     // C aliases A: one CTA must own all N columns of its rows (N == 128 == BN)
     launch_cfg<GemmCfg64x128>(a, stream);

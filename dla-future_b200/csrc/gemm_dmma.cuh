@@ -226,8 +226,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(co
 using GemmCfg128 = GemmCfg<128, 128, 16, 4, 1>;
 using GemmCfg64x128 = GemmCfg<64, 128, 16, 4, 2>;
 using GemmCfg64 = GemmCfg<64, 64, 16, 4, 2>;
+using GemmCfg128k32 = GemmCfg<128, 128, 32, 3, 1>;  // half the barriers per tile
+using GemmCfg128x64 = GemmCfg<128, 64, 16, 4, 2>;
 
-// Host launcher (defined in gemm_dmma.cu).
+// Host launcher (defined in gemm_dmma.cu): picks the tile configuration.
 void launch_gemm_nt_f64(const GemmArgs& args, cudaStream_t stream);
+// Explicit configuration (tools / A-B measurements): 0 = 128x128x16x4, 1 = 64x128 (2 CTA/SM), 2 = 64x64,
+// 3 = 128x128x32x3, 4 = 128x64 (2 CTA/SM).
+void launch_gemm_nt_f64_cfg(const GemmArgs& args, int cfg, cudaStream_t stream);
 
 }  // namespace dlaf_b200

@@ -244,6 +244,16 @@ int main() {
       double ms = time_ms(e0, e1) / reps;
       double fl = 2.0 * s.M * (double)s.N * s.K * (s.mask ? 0.5 * (1.0 + 128.0 / s.N) : 1.0);
       std::printf("gemm_nt_f64 %dx%dx%d mask %d: %.3f ms  %.2f TFLOP/s\n", s.M, s.N, s.K, s.mask, ms, fl / ms / 1e9);
+      for (int cfg : {1, 3, 4}) {
+        if (s.M * (long)s.N < 8192L * 8192L) break;
+        launch_gemm_nt_f64_cfg(g, cfg, 0);
+        cudaEventRecord(e0);
+        for (int i = 0; i < reps; ++i) launch_gemm_nt_f64_cfg(g, cfg, 0);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        DLAF_CUDA_CHECK(cudaGetLastError());
+        double msc = time_ms(e0, e1) / reps;
+        std::printf("   cfg %d: %.3f ms  %.2f TFLOP/s\n", cfg, msc, fl / msc / 1e9);
+      }
       if (!s.mask) {
         const double al = -1, be = 1;
         cublasDgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, s.M, s.N, s.K, &al, dP, s.M, dP, s.M, &be, dC, s.M);

@@ -34,11 +34,14 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
   int least, greatest;
   DLAF_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
   DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sH_, cudaStreamNonBlocking, greatest));
+  DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sM_, cudaStreamNonBlocking, greatest));
   DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sL_, cudaStreamNonBlocking, least));
   DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start_, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evP_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evB_[i], cudaEventDisableTiming));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evC_[i], cudaEventDisableTiming));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evD_[i], cudaEventDisableTiming));
   }
   const size_t wsz = static_cast<size_t>(ns_) * G * G;
   const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
@@ -61,8 +64,11 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
 template <class T>
 PotrfEngine<T>::~PotrfEngine() {
   cudaStreamSynchronize(sH_);
+  cudaStreamSynchronize(sM_);
   cudaStreamSynchronize(sL_);
   for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(evC_[i]);
+    cudaEventDestroy(evD_[i]);
     cudaFree(wbuf_[i]);
     cudaFree(diagbuf_[i]);
     cudaFree(panel_[i]);
@@ -77,6 +83,7 @@ PotrfEngine<T>::~PotrfEngine() {
   cudaFree(d_info_);
   cudaFreeHost(h_info_);
   cudaStreamDestroy(sH_);
+  cudaStreamDestroy(sM_);
   cudaStreamDestroy(sL_);
 }
 
@@ -263,7 +270,7 @@ void PotrfEngine<T>::trsm_panel(T* b, long ldb, int m, const T* tkk, long ldt, c
 // P_k on stream H: diagonal tile, its broadcast down the owning process column, the panel TRSM, and
 // the two panel broadcasts (row-wise, then "transposed" column-wise: broadcast_panel.h:107-188).
 template <class T>
-void PotrfEngine<T>::panel_step(int k) {
+void PotrfEngine<T>::panel_step(int k, bool wait_column) {
   using NT = NcclType<T>;
   const int P = geo_.P, Q = geo_.Q;
   const int owner_r = k % P, owner_c = k % Q;
@@ -300,8 +307,11 @@ void PotrfEngine<T>::panel_step(int k) {
       ldt = ld_;
       w = wbuf_[slot];
     }
-    if (mt > 0)
+    if (mt > 0) {
+      if (wait_column)  // rows of block column k below the diagonal tile: updated on stream M
+        DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evC_[(k - 1) % 2], 0));
       trsm_panel(tile_ptr(li1, lkc), ld_, mt * nbp_, tkk, ldt, w, sH_);
+    }
   }
 
   if (k < nt_ - 1 && P * Q > 1) {
@@ -332,17 +342,19 @@ void PotrfEngine<T>::panel_step(int k) {
   DLAF_CUDA_CHECK(cudaEventRecord(evP_[slot], sH_));
 }
 
-// U_k: trailing update of my local tiles with panel k. lookahead = only block column k+1 (if mine),
-// otherwise everything to the right of it.
+// U_k: trailing update of my local tiles with panel k.
+//   kBulk            everything to the right of block column k+1
+//   kNextDiag        only the diagonal tile (k+1, k+1) (if mine) — all the next potrf waits for
+//   kNextColumnRest  block column k+1 below its diagonal tile (if mine) — what the next TRSM waits for
 template <class T>
-void PotrfEngine<T>::update(int k, bool lookahead, cudaStream_t st) {
+void PotrfEngine<T>::update(int k, UpdatePart part, cudaStream_t st) {
   const int P = geo_.P, Q = geo_.Q;
   const int li1 = cnt_rows(k + 1), lj1 = cnt_cols(k + 1);
   if (ltr_ - li1 <= 0 || ltc_ - lj1 <= 0)
     return;
   const bool own_next = ((k + 1) % Q == geo_.pcol);
   int cj0, ncols;
-  if (lookahead) {
+  if (part != kBulk) {
     if (!own_next)
       return;
     cj0 = lj1;
@@ -355,8 +367,20 @@ void PotrfEngine<T>::update(int k, bool lookahead, cudaStream_t st) {
   if (ncols <= 0)
     return;
   const long gj0 = static_cast<long>(cj0) * Q + geo_.pcol;
-  const int ri0 = cnt_rows(gj0);  // first local row tile on or below the diagonal of column cj0
-  const int mrows = (ltr_ - ri0) * nbp_;
+  int ri0 = cnt_rows(gj0);  // first local row tile on or below the diagonal of column cj0
+  int mrows = (ltr_ - ri0) * nbp_;
+  if (part != kBulk) {
+    const bool own_diag = ((k + 1) % P == geo_.prow);  // then local row ri0 is global row k+1
+    if (part == kNextDiag) {
+      if (!own_diag)
+        return;
+      mrows = nbp_;
+    }
+    else if (own_diag) {
+      ri0 += 1;
+      mrows -= nbp_;
+    }
+  }
   if (mrows <= 0)
     return;
   const int slot = k % 2;
@@ -402,7 +426,7 @@ void PotrfEngine<T>::update(int k, bool lookahead, cudaStream_t st) {
     }
     a.ldb = nbp_;
   }
-  if (profiling_ && !lookahead) {
+  if (profiling_ && part == kBulk) {
     // algorithmic flops of this launch: 2 nbp^3 per off-diagonal tile, nbp^3 per diagonal tile
     // (herk), counted on global tile indices; complex: x4 (6 mul + 2 add per complex mac = 8 flop)
     double tiles = 0;
@@ -449,7 +473,8 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(sL_, ev_start_, 0));
   DLAF_CUDA_CHECK(cudaMemsetAsync(d_info_, 0, sizeof(int), sH_));
 
-  panel_step(0);
+  DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, ev_start_, 0));
+  panel_step(0, false);
   for (int k = 0; k < nt_ - 1; ++k) {
     // bulk of U_k on the low-priority stream
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sL_, evP_[k % 2], 0));
@@ -464,24 +489,32 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
       }
       const long before = launches_;
       DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_], sL_));
-      update(k, false, sL_);
+      update(k, kBulk, sL_);
       DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_ + 1], sL_));
       prof_flops_[prof_used_] = (launches_ > before) ? last_update_flops_ : -1.0;
       ++prof_used_;
     }
     else {
-      update(k, false, sL_);
+      update(k, kBulk, sL_);
     }
     DLAF_CUDA_CHECK(cudaEventRecord(evB_[k % 2], sL_));
-    // critical path on the high-priority stream: U_k(k+1), then P_{k+1}
+    // stream M: block column k+1 below its diagonal tile (needs panel k and the bulk of step k-1)
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, evP_[k % 2], 0));
+    if (k >= 1)
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, evB_[(k - 1) % 2], 0));
+    update(k, kNextColumnRest, sM_);
+    DLAF_CUDA_CHECK(cudaEventRecord(evC_[k % 2], sM_));
+    // critical path on stream H: the diagonal tile (k+1,k+1), then P_{k+1} (its TRSM waits for stream M)
     if (k >= 1)
       DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evB_[(k - 1) % 2], 0));
-    update(k, true, sH_);
-    panel_step(k + 1);
+    update(k, kNextDiag, sH_);
+    panel_step(k + 1, true);
   }
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evP_[(nt_ - 1) % 2], 0));
-  if (nt_ >= 2)
+  if (nt_ >= 2) {
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evB_[(nt_ - 2) % 2], 0));
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evC_[(nt_ - 2) % 2], 0));
+  }
   DLAF_CUDA_CHECK(cudaMemcpyAsync(h_info_, d_info_, sizeof(int), cudaMemcpyDeviceToHost, s));
 }
 

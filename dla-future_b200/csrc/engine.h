@@ -10,9 +10,12 @@
 //
 // Dependencies per step k (P_k = diagonal tile + panel of column k, U_k(j) = update of block column j
 // with panel k):   P_k <- U_{k-1}(k);   U_k(j) <- P_k, U_{k-1}(j).
-// Stream H (high priority):  U_{k-1}(k), P_k, broadcasts of panel k      — the critical path
-// Stream L (low priority):   U_k(k+2 ..)                                 — the bulk, ~95 % of the flops
-// which is exactly the reference's 1-column look-ahead priority rule (impl.h:171-173, :280-281).
+// Stream H (highest priority): U_{k-1}(k,k) (diagonal tile only), potrf of tile k, its broadcast, the
+//                              panel TRSM and the panel broadcasts     — the critical path
+// Stream M (highest priority): U_{k-1}(k) below the diagonal tile      — overlaps the potrf of tile k
+// Stream L (lowest priority):  U_k(k+2 ..)                             — the bulk, ~95 % of the flops
+// which is the reference's 1-column look-ahead priority rule (impl.h:171-173, :280-281) with the
+// diagonal tile split off so that it never waits for the rest of its column.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -86,8 +89,9 @@ public:
   void read_profile(double out[3]);
 
 private:
-  void panel_step(int k);
-  void update(int k, bool lookahead, cudaStream_t st);
+  void panel_step(int k, bool wait_column);
+  enum UpdatePart { kBulk = 0, kNextDiag = 1, kNextColumnRest = 2 };
+  void update(int k, UpdatePart part, cudaStream_t st);
   void factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_t st);
   void trsm_panel(T* b, long ldb, int m, const T* tkk, long ldt, const T* w, cudaStream_t st);
   void gemm(const GemmArgsT<T>& a, cudaStream_t st);
@@ -106,8 +110,9 @@ private:
   long own_ld_ = 0;
   bool external_ = false;
 
-  cudaStream_t sH_ = nullptr, sL_ = nullptr;
-  cudaEvent_t ev_start_ = nullptr, evP_[2] = {nullptr, nullptr}, evB_[2] = {nullptr, nullptr};
+  cudaStream_t sH_ = nullptr, sM_ = nullptr, sL_ = nullptr;
+  cudaEvent_t ev_start_ = nullptr, evP_[2] = {nullptr, nullptr}, evB_[2] = {nullptr, nullptr},
+              evC_[2] = {nullptr, nullptr}, evD_[2] = {nullptr, nullptr};
   T* wbuf_[2] = {nullptr, nullptr};     // inverses of the diagonal blocks (1 x 1 column grid)
   T* diagbuf_[2] = {nullptr, nullptr};  // diagonal tile + inverses, broadcast down the process column
   T* panel_[2] = {nullptr, nullptr};    // column panel, tile-contiguous

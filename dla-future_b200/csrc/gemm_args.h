@@ -28,6 +28,7 @@ struct GemmArgsT {
   // Panel<..> with AllocationLayout::Tiles, matrix/panel.h:392): row r of A lives at
   // A + (r / nbp) * a_ts + r % nbp. 0 = plain column-major operand.
   long a_ts, b_ts;
+  int dbg_stagger_ns;  // measurement aid: delay the second resident wave of CTAs by this many ns
 };
 
 // Tile classification against the lower-triangular mask.

@@ -22,16 +22,6 @@ void launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   DLAF_CUDA_CHECK(cudaGetLastError());
 }
 
-int sm_count() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
-}
-
 }  // namespace
 
 void launch_gemm_nt_f64_cfg(const GemmArgs& a, int cfg, cudaStream_t stream) {
@@ -41,6 +31,9 @@ void launch_gemm_nt_f64_cfg(const GemmArgs& a, int cfg, cudaStream_t stream) {
     case 2: launch_cfg<GemmCfg64>(a, stream); break;
     case 3: launch_cfg<GemmCfg128k32>(a, stream); break;
     case 4: launch_cfg<GemmCfg128x64>(a, stream); break;
+    case 5: launch_cfg<GemmCfg64w4s3>(a, stream); break;
+    case 6: launch_cfg<GemmCfg64w4s4>(a, stream); break;
+    case 7: launch_cfg<GemmCfg32x128w4>(a, stream); break;
     default: DLAF_B200_ASSERT(false, "unknown gemm configuration");
   }
 }
@@ -57,24 +50,21 @@ void launch_gemm_nt_f64(const GemmArgs& a, cudaStream_t stream) {
                        (reinterpret_cast<uintptr_t>(a.C) & 15) == 0,
                    "16-byte aligned operands");
   DLAF_B200_ASSERT(a.a_ts % 2 == 0 && a.b_ts % 2 == 0, "16-byte aligned panel tiles");
-  // Tile choice: a problem that cannot fill the GPU with 128x128 tiles is latency-bound (it sits on
-  // the critical path of the factorization), so spread it over 2x / 4x more CTAs.
-  long ctas = static_cast<long>(a.M / 128) * (a.N / 128);
-  if (a.mask == kMaskLower && a.M == a.N)
-    ctas = ctas / 2 + a.M / 256;
-  const bool in_place = (static_cast<const void*>(a.A) == static_cast<const void*>(a.C));
-  DLAF_B200_ASSERT(!in_place || a.N == 128, "in-place product needs one CTA column");
+  // Tile choice (measured, profiles/r01_kernel_test_6_4warp_ctas.log): 64x64 tiles on 4-warp CTAs, four
+  // resident per SM, beat the classic 128x128 / 8-warp tile (33.9 vs 29.4 TFLOP/s): barriers, pipeline
+  // fill and epilogue of one CTA are covered by the other three. The same kernel serves the small
+  // latency-critical GEMMs of the panel chain (4x more CTAs than 128x128 tiles).
   static const int bulk_cfg = [] {
     const char* e = std::getenv("DLAF_B200_GEMM_BULK_CFG");
-    return e ? std::atoi(e) : 1;  // 64x128, two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+    return e ? std::atoi(e) : 5;
   }();
-  if (ctas >= sm_count())
-    launch_gemm_nt_f64_cfg(a, bulk_cfg, stream);
-  else if (in_place)
+  const bool in_place = (static_cast<const void*>(a.A) == static_cast<const void*>(a.C));
+  DLAF_B200_ASSERT(!in_place || a.N == 128, "in-place product needs one CTA column");
+  if (in_place)
     // C aliases A: one CTA must own all N columns of its rows (N == 128 == BN)
-    launch_cfg<GemmCfg64x128>(a, stream);
+    launch_cfg<GemmCfg32x128w4>(a, stream);
   else
-    launch_cfg<GemmCfg64>(a, stream);
+    launch_gemm_nt_f64_cfg(a, bulk_cfg, stream);
 }
 
 template <>

@@ -47,10 +47,10 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 }  // namespace gemm_detail
 
-template <int BM_, int BN_, int BK_, int STAGES_, int MINB_ = 1>
+template <int BM_, int BN_, int BK_, int STAGES_, int MINB_ = 1, int WARPS_M_ = 2, int WARPS_N_ = 4>
 struct GemmCfg {
   static constexpr int BM = BM_, BN = BN_, BK = BK_, STAGES = STAGES_, MINB = MINB_;
-  static constexpr int THREADS = 256;
+  static constexpr int THREADS = 32 * WARPS_M_ * WARPS_N_;
   // +4 doubles of padding: the DMMA fragment read (k = lane&3, m = lane>>2) then hits 16 distinct
   // 8-byte banks per half-warp (row stride == 4 mod 16 doubles) -> conflict-free LDS.64.
   static constexpr int LDA_S = BM + 4, LDB_S = BN + 4;
@@ -58,7 +58,7 @@ struct GemmCfg {
   static constexpr int LDC_S = BM + 2;  // epilogue staging tile (reuses the operand ring)
   static constexpr int RING_BYTES = STAGES * (A_STAGE + B_STAGE) * 8;
   static constexpr int SMEM_BYTES = RING_BYTES > BN * LDC_S * 8 ? RING_BYTES : BN * LDC_S * 8;
-  static constexpr int WARPS_M = 2, WARPS_N = 4;
+  static constexpr int WARPS_M = WARPS_M_, WARPS_N = WARPS_N_;
   static constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;  // warp tile
   static constexpr int FM = WM / 8, FN = WN / 8;              // 8x8 fragments per warp
 };
@@ -79,6 +79,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(co
   if (cls == 0)
     return;
 
+  if (p.dbg_stagger_ns > 0) {
+    const unsigned lin = blockIdx.x + blockIdx.y * gridDim.x;
+    if (lin >= 148 && lin < 296)
+      __nanosleep(p.dbg_stagger_ns);
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
   const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM;
@@ -228,11 +233,17 @@ using GemmCfg64x128 = GemmCfg<64, 128, 16, 4, 2>;
 using GemmCfg64 = GemmCfg<64, 64, 16, 4, 2>;
 using GemmCfg128k32 = GemmCfg<128, 128, 32, 3, 1>;  // half the barriers per tile
 using GemmCfg128x64 = GemmCfg<128, 64, 16, 4, 2>;
+// 4-warp CTAs: 4 (3 stages) or 3 (4 stages) independent CTAs per SM -> barriers, prologues and epilogues
+// of one CTA are covered by the three others.
+using GemmCfg64w4s3 = GemmCfg<64, 64, 16, 3, 4, 2, 2>;
+using GemmCfg64w4s4 = GemmCfg<64, 64, 16, 4, 3, 2, 2>;
+using GemmCfg32x128w4 = GemmCfg<32, 128, 16, 3, 4, 1, 4>;  // in-place products (one CTA owns all 128 columns)
 
 // Host launcher (defined in gemm_dmma.cu): picks the tile configuration.
 void launch_gemm_nt_f64(const GemmArgs& args, cudaStream_t stream);
 // Explicit configuration (tools / A-B measurements): 0 = 128x128x16x4, 1 = 64x128 (2 CTA/SM), 2 = 64x64,
-// 3 = 128x128x32x3, 4 = 128x64 (2 CTA/SM).
+// 3 = 128x128x32x3, 4 = 128x64 (2 CTA/SM), 5 = 64x64/4 warps/3 stages (4 CTA/SM), 6 = same/4 stages (3 CTA/SM),
+// 7 = 32x128/4 warps (in-place products).
 void launch_gemm_nt_f64_cfg(const GemmArgs& args, int cfg, cudaStream_t stream);
 
 }  // namespace dlaf_b200

@@ -244,15 +244,18 @@ int main() {
       double ms = time_ms(e0, e1) / reps;
       double fl = 2.0 * s.M * (double)s.N * s.K * (s.mask ? 0.5 * (1.0 + 128.0 / s.N) : 1.0);
       std::printf("gemm_nt_f64 %dx%dx%d mask %d: %.3f ms  %.2f TFLOP/s\n", s.M, s.N, s.K, s.mask, ms, fl / ms / 1e9);
-      for (int cfg : {1, 3, 4}) {
+      for (int cfg : {1, 5, 6}) {
         if (s.M * (long)s.N < 8192L * 8192L) break;
+        g.dbg_stagger_ns = 0;
+        if (cfg == 101) { g.dbg_stagger_ns = 30000; cfg = 1; }
         launch_gemm_nt_f64_cfg(g, cfg, 0);
         cudaEventRecord(e0);
         for (int i = 0; i < reps; ++i) launch_gemm_nt_f64_cfg(g, cfg, 0);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         DLAF_CUDA_CHECK(cudaGetLastError());
         double msc = time_ms(e0, e1) / reps;
-        std::printf("   cfg %d: %.3f ms  %.2f TFLOP/s\n", cfg, msc, fl / msc / 1e9);
+        std::printf("   cfg %d stagger %d ns: %.3f ms  %.2f TFLOP/s\n", cfg, g.dbg_stagger_ns, msc, fl / msc / 1e9);
+        g.dbg_stagger_ns = 0;
       }
       if (!s.mask) {
         const double al = -1, be = 1;

@@ -318,11 +318,18 @@ int cholesky_host(int ctx, char uplo, T* a, const DLAF_descriptor& desc) {
   cudaStream_t s = ctx_stream(c);
   if (u.n > 0 && u.lrows > 0 && u.lcols > 0) {
     if (!upper && !eng.padded()) {
-      // tiles need no padding: the slab IS the user layout, copy straight into it
+      // tiles need no padding: the slab IS the user layout. Pipelined: chunked upload of the referenced
+      // triangle overlapping the first steps, every block column downloaded as soon as it is final.
+      static const bool serial = std::getenv("DLAF_B200_HOST_SERIAL") != nullptr;
       D* slab = eng.slab();
-      copy_triangle<D>(true, false, u, host, desc.ld, slab, eng.slab_ld(), s);
-      eng.factorize(s);
-      copy_triangle<D>(false, false, u, host, desc.ld, slab, eng.slab_ld(), s);
+      if (serial) {
+        copy_triangle<D>(true, false, u, host, desc.ld, slab, eng.slab_ld(), s);
+        eng.factorize(s);
+        copy_triangle<D>(false, false, u, host, desc.ld, slab, eng.slab_ld(), s);
+      }
+      else {
+        eng.factorize_host(host, desc.ld, s);
+      }
     }
     else {
       const long lds = round_up(u.lrows, 2);

@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "comm.h"
 #include "common.h"
@@ -77,6 +78,18 @@ PotrfEngine<T>::~PotrfEngine() {
     cudaEventDestroy(evB_[i]);
   }
   cudaEventDestroy(ev_start_);
+  for (auto e : evIn_)
+    cudaEventDestroy(e);
+  for (auto e : evBc_)
+    cudaEventDestroy(e);
+  for (size_t c = 1; c < sLc_.size(); ++c)
+    cudaStreamDestroy(sLc_[c]);
+  if (evOut_)
+    cudaEventDestroy(evOut_);
+  if (sIn_)
+    cudaStreamDestroy(sIn_);
+  if (sOut_)
+    cudaStreamDestroy(sOut_);
   for (auto e : prof_ev_)
     cudaEventDestroy(e);
   cudaFree(own_slab_);
@@ -283,6 +296,7 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
   const int slot = k % 2;
 
   if (in_col) {
+    wait_columns(lkc + 1, sH_);
     const T* tkk = nullptr;
     long ldt = 0;
     const T* w = nullptr;
@@ -340,49 +354,17 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
     }
   }
   DLAF_CUDA_CHECK(cudaEventRecord(evP_[slot], sH_));
+  if (in_col)
+    download_column(lkc, evP_[slot]);  // block column k is final on this rank
 }
 
-// U_k: trailing update of my local tiles with panel k.
-//   kBulk            everything to the right of block column k+1
-//   kNextDiag        only the diagonal tile (k+1, k+1) (if mine) — all the next potrf waits for
-//   kNextColumnRest  block column k+1 below its diagonal tile (if mine) — what the next TRSM waits for
+// U_k on my local block columns [cj0, cj0 + ncols), rows from local tile row ri0 on (mrows elements):
+// ONE masked GEMM launch.
 template <class T>
-void PotrfEngine<T>::update(int k, UpdatePart part, cudaStream_t st) {
+void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows, bool count_flops, cudaStream_t st) {
   const int P = geo_.P, Q = geo_.Q;
   const int li1 = cnt_rows(k + 1), lj1 = cnt_cols(k + 1);
-  if (ltr_ - li1 <= 0 || ltc_ - lj1 <= 0)
-    return;
-  const bool own_next = ((k + 1) % Q == geo_.pcol);
-  int cj0, ncols;
-  if (part != kBulk) {
-    if (!own_next)
-      return;
-    cj0 = lj1;
-    ncols = 1;
-  }
-  else {
-    cj0 = own_next ? lj1 + 1 : lj1;
-    ncols = ltc_ - cj0;
-  }
-  if (ncols <= 0)
-    return;
   const long gj0 = static_cast<long>(cj0) * Q + geo_.pcol;
-  int ri0 = cnt_rows(gj0);  // first local row tile on or below the diagonal of column cj0
-  int mrows = (ltr_ - ri0) * nbp_;
-  if (part != kBulk) {
-    const bool own_diag = ((k + 1) % P == geo_.prow);  // then local row ri0 is global row k+1
-    if (part == kNextDiag) {
-      if (!own_diag)
-        return;
-      mrows = nbp_;
-    }
-    else if (own_diag) {
-      ri0 += 1;
-      mrows -= nbp_;
-    }
-  }
-  if (mrows <= 0)
-    return;
   const int slot = k % 2;
   const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
   const int lkc = k / Q;
@@ -426,11 +408,11 @@ void PotrfEngine<T>::update(int k, UpdatePart part, cudaStream_t st) {
     }
     a.ldb = nbp_;
   }
-  if (profiling_ && part == kBulk) {
+  if (profiling_ && count_flops) {
     // algorithmic flops of this launch: 2 nbp^3 per off-diagonal tile, nbp^3 per diagonal tile
     // (herk), counted on global tile indices; complex: x4 (6 mul + 2 add per complex mac = 8 flop)
     double tiles = 0;
-    for (int lj = cj0; lj < ltc_; ++lj) {
+    for (int lj = cj0; lj < cj0 + ncols; ++lj) {
       const long gj = static_cast<long>(lj) * Q + geo_.pcol;
       for (int li = ri0; li < ltr_; ++li) {
         const long gi = static_cast<long>(li) * P + geo_.prow;
@@ -441,9 +423,152 @@ void PotrfEngine<T>::update(int k, UpdatePart part, cudaStream_t st) {
       }
     }
     const double cplx = (sizeof(T) == 2 * sizeof(base_t<T>)) ? 4.0 : 1.0;
-    last_update_flops_ = tiles * cplx * static_cast<double>(nbp_) * nbp_ * nbp_;
+    last_update_flops_ += tiles * cplx * static_cast<double>(nbp_) * nbp_ * nbp_;
   }
   gemm(a, st);
+}
+
+// U_k: trailing update of my local tiles with panel k.
+//   kBulk            everything to the right of block column k+1
+//   kNextDiag        only the diagonal tile (k+1, k+1) (if mine) — all the next potrf waits for
+//   kNextColumnRest  block column k+1 below its diagonal tile (if mine) — what the next TRSM waits for
+template <class T>
+void PotrfEngine<T>::update(int k, UpdatePart part, cudaStream_t st) {
+  const int P = geo_.P, Q = geo_.Q;
+  const int li1 = cnt_rows(k + 1), lj1 = cnt_cols(k + 1);
+  last_update_flops_ = 0.0;
+  if (ltr_ - li1 <= 0 || ltc_ - lj1 <= 0)
+    return;
+  const bool own_next = ((k + 1) % Q == geo_.pcol);
+  int cj0, ncols;
+  if (part != kBulk) {
+    if (!own_next)
+      return;
+    cj0 = lj1;
+    ncols = 1;
+  }
+  else {
+    cj0 = own_next ? lj1 + 1 : lj1;
+    ncols = ltc_ - cj0;
+  }
+  if (ncols <= 0)
+    return;
+  auto first_row = [&](int lj) { return cnt_rows(static_cast<long>(lj) * Q + geo_.pcol); };
+  int ri0 = first_row(cj0);  // first local row tile on or below the diagonal of column cj0
+  int mrows = (ltr_ - ri0) * nbp_;
+  if (part != kBulk) {
+    const bool own_diag = ((k + 1) % P == geo_.prow);  // then local row ri0 is global row k+1
+    if (part == kNextDiag) {
+      if (!own_diag)
+        return;
+      mrows = nbp_;
+    }
+    else if (own_diag) {
+      ri0 += 1;
+      mrows -= nbp_;
+    }
+  }
+  if (mrows <= 0)
+    return;
+  const int cend = cj0 + ncols;
+  wait_columns(cend, st);
+  launch_update(k, cj0, ncols, ri0, mrows, part == kBulk, st);
+}
+
+// ---- host pipelining (factorize_host) -------------------------------------------------------------
+template <class T>
+int PotrfEngine<T>::chunk_of(int lj) const {
+  if (in_end_.empty())
+    return 0;
+  size_t c = 0;
+  while (c + 1 < in_end_.size() && in_end_[c] <= lj)
+    ++c;
+  return static_cast<int>(c);
+}
+
+template <class T>
+void PotrfEngine<T>::wait_bulk(int k, int lj, cudaStream_t st) {
+  const int nc = nchunks();
+  if (geo_.P * geo_.Q > 1 || lj < 0) {
+    // distributed: the panel workspaces of step k are shared by all chunks -> wait for all of them
+    for (int c = 0; c < nc; ++c)
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[2 * c + k % 2], 0));
+  }
+  else {
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[2 * chunk_of(lj) + k % 2], 0));
+  }
+}
+
+template <class T>
+void PotrfEngine<T>::issue_uploads() {
+  // one 2D copy per local block column (rows from its diagonal tile down), grouped into chunks of
+  // ~256 MB; an event per chunk. The copy stream is in order, so chunk c resident => chunks < c resident.
+  const size_t chunk_bytes = size_t(256) << 20;
+  const int nb = geo_.nb;
+  in_end_.clear();
+  size_t acc = 0, used = 0;
+  for (int lj = 0; lj < ltc_; ++lj) {
+    const long gj = static_cast<long>(lj) * geo_.Q + geo_.pcol;
+    const int ri = cnt_rows(gj);
+    const long rows = static_cast<long>(ltr_ - ri) * nb;
+    if (rows > 0) {
+      const T* h = host_ + static_cast<long>(ri) * nb + static_cast<long>(lj) * nb * ldh_;
+      DLAF_CUDA_CHECK(cudaMemcpy2DAsync(tile_ptr(ri, lj), sizeof(T) * ld_, h, sizeof(T) * ldh_, sizeof(T) * rows, nb,
+                                        cudaMemcpyHostToDevice, sIn_));
+      acc += sizeof(T) * rows * nb;
+    }
+    if (acc >= chunk_bytes || lj == ltc_ - 1) {
+      if (evIn_.size() <= used) {
+        cudaEvent_t e;
+        DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evIn_.push_back(e);
+      }
+      DLAF_CUDA_CHECK(cudaEventRecord(evIn_[used], sIn_));
+      in_end_.push_back(lj + 1);
+      ++used;
+      acc = 0;
+    }
+  }
+}
+
+template <class T>
+void PotrfEngine<T>::wait_columns(int lj_end, cudaStream_t st) {
+  if (host_ == nullptr || lj_end <= 0 || in_end_.empty())
+    return;
+  size_t c = 0;
+  while (c + 1 < in_end_.size() && in_end_[c] < lj_end)
+    ++c;
+  DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evIn_[c], 0));
+}
+
+template <class T>
+void PotrfEngine<T>::download_column(int lj, cudaEvent_t final_ev) {
+  if (host_ == nullptr)
+    return;
+  const int nb = geo_.nb;
+  const long gj = static_cast<long>(lj) * geo_.Q + geo_.pcol;
+  const int ri = cnt_rows(gj);
+  const long rows = static_cast<long>(ltr_ - ri) * nb;
+  if (rows <= 0)
+    return;
+  DLAF_CUDA_CHECK(cudaStreamWaitEvent(sOut_, final_ev, 0));
+  T* h = host_ + static_cast<long>(ri) * nb + static_cast<long>(lj) * nb * ldh_;
+  DLAF_CUDA_CHECK(cudaMemcpy2DAsync(h, sizeof(T) * ldh_, tile_ptr(ri, lj), sizeof(T) * ld_, sizeof(T) * rows, nb,
+                                    cudaMemcpyDeviceToHost, sOut_));
+}
+
+template <class T>
+void PotrfEngine<T>::factorize_host(T* host, long ldh, cudaStream_t s) {
+  DLAF_B200_ASSERT(!external_ && !padded(), "pipelined host path needs unpadded tiles in the engine's slab");
+  if (sIn_ == nullptr) {
+    DLAF_CUDA_CHECK(cudaStreamCreateWithFlags(&sIn_, cudaStreamNonBlocking));
+    DLAF_CUDA_CHECK(cudaStreamCreateWithFlags(&sOut_, cudaStreamNonBlocking));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evOut_, cudaEventDisableTiming));
+  }
+  host_ = host;
+  ldh_ = ldh;
+  factorize(s);
+  host_ = nullptr;
 }
 
 template <class T>
@@ -474,45 +599,101 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   DLAF_CUDA_CHECK(cudaMemsetAsync(d_info_, 0, sizeof(int), sH_));
 
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, ev_start_, 0));
+  if (host_) {
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sIn_, ev_start_, 0));
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sOut_, ev_start_, 0));
+    issue_uploads();
+  }
+  else {
+    // device-resident: column chunks of equal width (DLAF_B200_BULK_CHUNKS, default 1 = one bulk launch per step)
+    static const int want = [] {
+      const char* e = std::getenv("DLAF_B200_BULK_CHUNKS");
+      return e ? std::atoi(e) : 1;
+    }();
+    in_end_.clear();
+    const int nc_res = want < 1 ? 1 : (want > ltc_ ? (ltc_ > 0 ? ltc_ : 1) : want);
+    for (int c = 1; c <= nc_res; ++c)
+      in_end_.push_back(static_cast<int>(static_cast<long>(ltc_) * c / nc_res));
+  }
+  // bulk streams / events, one per column chunk
+  const int nc = nchunks();
+  if (sLc_.empty())
+    sLc_.push_back(sL_);
+  while (static_cast<int>(sLc_.size()) < nc) {
+    int least, greatest;
+    cudaStream_t st;
+    DLAF_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, least));
+    sLc_.push_back(st);
+  }
+  while (static_cast<int>(evBc_.size()) < 2 * nc) {
+    cudaEvent_t e;
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    evBc_.push_back(e);
+  }
+  for (int c = 1; c < nc; ++c)
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sLc_[c], ev_start_, 0));
+
   panel_step(0, false);
   for (int k = 0; k < nt_ - 1; ++k) {
-    // bulk of U_k on the low-priority stream
-    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sL_, evP_[k % 2], 0));
-    if (profiling_) {
-      if (prof_ev_.size() < 2 * (prof_used_ + 1)) {
-        cudaEvent_t a, b;
-        DLAF_CUDA_CHECK(cudaEventCreate(&a));
-        DLAF_CUDA_CHECK(cudaEventCreate(&b));
-        prof_ev_.push_back(a);
-        prof_ev_.push_back(b);
-        prof_flops_.push_back(0.0);
+    // bulk of U_k on the low-priority stream(s), one launch per column chunk
+    const int lj1 = cnt_cols(k + 1);
+    const bool own_next = ((k + 1) % geo_.Q == geo_.pcol);
+    const int bulk_c0 = own_next ? lj1 + 1 : lj1;
+    for (int c = 0; c < nc; ++c) {
+      cudaStream_t st = sLc_[c];
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evP_[k % 2], 0));
+      const int cbeg = (nc == 1) ? 0 : (c == 0 ? 0 : in_end_[c - 1]);
+      const int cend = (nc == 1) ? ltc_ : in_end_[c];
+      const int c0 = cbeg > bulk_c0 ? cbeg : bulk_c0;
+      const bool prof = profiling_ && nc == 1;
+      if (prof) {
+        if (prof_ev_.size() < 2 * (prof_used_ + 1)) {
+          cudaEvent_t a, b;
+          DLAF_CUDA_CHECK(cudaEventCreate(&a));
+          DLAF_CUDA_CHECK(cudaEventCreate(&b));
+          prof_ev_.push_back(a);
+          prof_ev_.push_back(b);
+          prof_flops_.push_back(0.0);
+        }
+        DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_], st));
       }
       const long before = launches_;
-      DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_], sL_));
-      update(k, kBulk, sL_);
-      DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_ + 1], sL_));
-      prof_flops_[prof_used_] = (launches_ > before) ? last_update_flops_ : -1.0;
-      ++prof_used_;
+      last_update_flops_ = 0.0;
+      if (c0 < cend && ltr_ - cnt_rows(k + 1) > 0) {
+        if (host_)
+          DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evIn_[c], 0));
+        const int r0 = cnt_rows(static_cast<long>(c0) * geo_.Q + geo_.pcol);
+        if (ltr_ - r0 > 0)
+          launch_update(k, c0, cend - c0, r0, (ltr_ - r0) * nbp_, true, st);
+      }
+      if (prof) {
+        DLAF_CUDA_CHECK(cudaEventRecord(prof_ev_[2 * prof_used_ + 1], st));
+        prof_flops_[prof_used_] = (launches_ > before) ? last_update_flops_ : -1.0;
+        ++prof_used_;
+      }
+      DLAF_CUDA_CHECK(cudaEventRecord(evBc_[2 * c + k % 2], st));
     }
-    else {
-      update(k, kBulk, sL_);
-    }
-    DLAF_CUDA_CHECK(cudaEventRecord(evB_[k % 2], sL_));
-    // stream M: block column k+1 below its diagonal tile (needs panel k and the bulk of step k-1)
+    // stream M: block column k+1 below its diagonal tile (needs panel k and the bulk of step k-1 there)
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, evP_[k % 2], 0));
     if (k >= 1)
-      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, evB_[(k - 1) % 2], 0));
+      wait_bulk(k - 1, own_next ? lj1 : -1, sM_);
     update(k, kNextColumnRest, sM_);
     DLAF_CUDA_CHECK(cudaEventRecord(evC_[k % 2], sM_));
     // critical path on stream H: the diagonal tile (k+1,k+1), then P_{k+1} (its TRSM waits for stream M)
     if (k >= 1)
-      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evB_[(k - 1) % 2], 0));
+      wait_bulk(k - 1, own_next ? lj1 : -1, sH_);
     update(k, kNextDiag, sH_);
     panel_step(k + 1, true);
   }
+  if (host_) {
+    DLAF_CUDA_CHECK(cudaEventRecord(evOut_, sOut_));
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evOut_, 0));
+  }
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evP_[(nt_ - 1) % 2], 0));
   if (nt_ >= 2) {
-    DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evB_[(nt_ - 2) % 2], 0));
+    for (int c = 0; c < nc; ++c)
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evBc_[2 * c + (nt_ - 2) % 2], 0));
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evC_[(nt_ - 2) % 2], 0));
   }
   DLAF_CUDA_CHECK(cudaMemcpyAsync(h_info_, d_info_, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -76,6 +76,12 @@ public:
   // --- the factorization: asynchronous w.r.t. the host; ordered after everything already enqueued on
   // `s` and complete (for stream order purposes) when `s` reaches the point after this call.
   void factorize(cudaStream_t s);
+  // Host-resident, pipelined (tiles without padding, lower): the referenced triangle of the caller's
+  // HOST local matrix is uploaded in block-column chunks on a copy stream while the factorization is
+  // already running (every kernel waits only for the chunks it touches), and every block column is
+  // downloaded as soon as its panel is final. Replaces the MatrixMirror bracket of the reference's C
+  // API (src/c_api/factorization/cholesky.h:48-53: whole-matrix H2D, factorization, whole-matrix D2H).
+  void factorize_host(T* host, long ldh, cudaStream_t s);
   // LAPACK-style info of the last factorize (0 = success, k = leading minor of order k not positive
   // definite). Synchronises `s`.
   int info(cudaStream_t s);
@@ -92,6 +98,7 @@ private:
   void panel_step(int k, bool wait_column);
   enum UpdatePart { kBulk = 0, kNextDiag = 1, kNextColumnRest = 2 };
   void update(int k, UpdatePart part, cudaStream_t st);
+  void launch_update(int k, int cj0, int ncols, int ri0, int mrows, bool count_flops, cudaStream_t st);
   void factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_t st);
   void trsm_panel(T* b, long ldb, int m, const T* tkk, long ldt, const T* w, cudaStream_t st);
   void gemm(const GemmArgsT<T>& a, cudaStream_t st);
@@ -117,6 +124,24 @@ private:
   T* diagbuf_[2] = {nullptr, nullptr};  // diagonal tile + inverses, broadcast down the process column
   T* panel_[2] = {nullptr, nullptr};    // column panel, tile-contiguous
   T* panelT_[2] = {nullptr, nullptr};   // transposed panel (tiles (j,k) for my local columns j)
+  // host pipelining state (factorize_host)
+  void issue_uploads();
+  void wait_columns(int lj_end, cudaStream_t st);  // block columns [0, lj_end) resident before `st` goes on
+  void download_column(int lj, cudaEvent_t final_ev);
+  T* host_ = nullptr;
+  long ldh_ = 0;
+  cudaStream_t sIn_ = nullptr, sOut_ = nullptr;
+  cudaEvent_t evOut_ = nullptr;
+  std::vector<cudaEvent_t> evIn_;
+  std::vector<int> in_end_;  // chunk c covers local block columns [in_end_[c-1], in_end_[c])
+  // Bulk updates run per column chunk, each chunk on its own low-priority stream (chunk 0 = sL_): a chunk
+  // only depends on its own history, so updates of early chunks proceed while later ones are still being
+  // uploaded. Device-resident runs use a single chunk.
+  std::vector<cudaStream_t> sLc_;
+  std::vector<cudaEvent_t> evBc_;  // [2*c + parity]
+  int chunk_of(int lj) const;
+  int nchunks() const { return in_end_.empty() ? 1 : static_cast<int>(in_end_.size()); }
+  void wait_bulk(int k, int lj, cudaStream_t st);  // bulk of step k done on the chunk of column lj (or on all)
   int* d_info_ = nullptr;
   int* h_info_ = nullptr;
   long launches_ = 0;

@@ -7,12 +7,12 @@ CSRC      := dla-future_b200/csrc
 LIBDIR    := dla-future_b200/lib
 LIB       := $(LIBDIR)/libdlaf_b200.so
 
-CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/potrf_tile.o build/layout.o build/engine.o build/peak.o
+CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/potrf_tile.o build/layout.o build/engine.o build/peak.o build/check.o
 CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
 OBJS     := $(CU_OBJS) $(CPP_OBJS)
 HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h)
 
-all: $(LIB) tools/gpu_kernel_test
+all: $(LIB) tools/gpu_kernel_test miniapp/miniapp_cholesky
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -30,6 +30,10 @@ $(LIB): $(OBJS)
 
 tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_tile.o $(HDRS)
 	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/potrf_tile.o -lcublas -o $@
+
+# The driver is plain C++ against include/dlaf (header-only surface) + the C-ABI library.
+miniapp/miniapp_cholesky: miniapp/miniapp_cholesky.cpp $(LIB) $(wildcard include/dlaf/*.h) $(wildcard include/dlaf/*/*.h)
+	g++ $(CXXFLAGS) $< -o $@ -L$(LIBDIR) -ldlaf_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread
 
 clean:
 	rm -rf build tools/gpu_kernel_test $(LIBDIR)/*.so

@@ -32,6 +32,7 @@ C_API_SYMBOLS = [
     *[f"dlaf_p{t}potrf" for t in "sdcz"],
     *[f"dlaf_b200_cholesky_factorization_device_{t}" for t in "sdcz"],
     *[f"dlaf_b200_set_random_hermitian_positive_definite_{t}" for t in "sdcz"],
+    *[f"dlaf_b200_check_cholesky_{t}" for t in "sdcz"], "dlaf_b200_grid_barrier",
     "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info",
     "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
@@ -127,6 +128,11 @@ def lib() -> ctypes.CDLL:
         f = getattr(L, f"dlaf_b200_set_random_hermitian_positive_definite_{t}")
         f.argtypes = [ci, vp, DLAF_descriptor]
         f.restype = None
+        f = getattr(L, f"dlaf_b200_check_cholesky_{t}")
+        f.argtypes = [ci, cc, vp, vp, DLAF_descriptor]
+        f.restype = ctypes.c_double
+    L.dlaf_b200_grid_barrier.argtypes = [ci]
+    L.dlaf_b200_grid_barrier.restype = None
     L.dlaf_b200_wait.argtypes = [ci, vp]
     L.dlaf_b200_wait.restype = ci
     L.dlaf_b200_last_launch_count.argtypes = [ci]
@@ -278,6 +284,19 @@ def set_random_hermitian_positive_definite(ctx: int, a: np.ndarray, n: int, nb: 
     d = descriptor(n, nb, _ld_of(a), isrc, jsrc)
     f = getattr(lib(), f"dlaf_b200_set_random_hermitian_positive_definite_{type_char(a.dtype)}")
     f(ctx, a.ctypes.data, d)
+
+
+def check_cholesky(ctx: int, uplo: str, a_orig: np.ndarray, factor: np.ndarray, nb: int) -> float:
+    """The miniapp's check (max|A - L L^H| / max|A| on the `uplo` triangle) evaluated on the GPU."""
+    n = a_orig.shape[0]
+    assert _ld_of(a_orig) == _ld_of(factor)
+    d = descriptor(n, nb, _ld_of(a_orig))
+    f = getattr(lib(), f"dlaf_b200_check_cholesky_{type_char(a_orig.dtype)}")
+    return f(ctx, uplo.encode(), a_orig.ctypes.data, factor.ctypes.data, d)
+
+
+def grid_barrier(ctx: int) -> None:
+    lib().dlaf_b200_grid_barrier(ctx)
 
 
 def total_ops(dtype, n: int) -> float:

@@ -391,6 +391,18 @@ void pxpotrf(char uplo, int n, T* a, int ia, int ja, const int desca[9], int* in
 }
 
 template <class T>
+double check_cholesky(int ctx, char uplo, const T* a, const T* f, const DLAF_descriptor& desc) {
+  using D = devtype_t<T>;
+  ensure_device();
+  GridCtx& c = grid_from_context(ctx);
+  if (c.grid->P * c.grid->Q != 1)
+    return -1.0;  // distributed check: not provided
+  is_upper(uplo);
+  return check_cholesky_single_rank<D>(uplo, desc.n, desc.nb, reinterpret_cast<const D*>(a), desc.ld,
+                                       reinterpret_cast<const D*>(f), desc.ld);
+}
+
+template <class T>
 void random_hpd(int ctx, T* a, const DLAF_descriptor& desc) {
   ensure_initialized();
   GridCtx& c = grid_from_context(ctx);
@@ -505,6 +517,10 @@ struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int 
   void dlaf_b200_set_random_hermitian_positive_definite_##sfx(int ctx, T* a,                                  \
                                                               struct DLAF_descriptor d) noexcept {            \
     random_hpd<T>(ctx, a, d);                                                                                 \
+  }                                                                                                           \
+  double dlaf_b200_check_cholesky_##sfx(int ctx, char uplo, const T* a, const T* f,                           \
+                                        struct DLAF_descriptor d) noexcept {                                  \
+    return check_cholesky<T>(ctx, uplo, a, f, d);                                                             \
   }
 
 DLAF_B200_DEFINE(d, double)
@@ -526,6 +542,14 @@ long dlaf_b200_last_launch_count(int ctx) noexcept {
   if (c.last_type < 0 || !c.slot[c.last_type])
     return 0;
   return c.slot[c.last_type]->launches();
+}
+
+void dlaf_b200_grid_barrier(int ctx) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  if (c.grid->P * c.grid->Q == 1 || !c.grid->in_grid)
+    return;
+  ensure_device();
+  reduce_info(c, 0, ctx_stream(c));  // a 1-int all-reduce + stream sync = barrier over the grid
 }
 
 void dlaf_b200_set_profiling(int ctx, int enable) noexcept {

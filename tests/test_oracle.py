@@ -124,3 +124,20 @@ def test_scatter_gather_roundtrip(oracle):
         for (p, q), loc in parts.items():
             assert loc.shape == (oracle.local_size(35, 4, grid[0], p, src[0]), oracle.local_size(35, 4, grid[1], q, src[1]))
         assert np.array_equal(oracle.gather_block_cyclic(parts, 35, 4, grid, np.float64, src), a)
+
+
+def test_headers_are_c_and_library_links_with_c_linkage(pkg, tmp_path):
+    """gcc (C, not C++) compiles the public headers and links the library — the reference does the same with
+    test/unit/c_api/factorization/test_cholesky_c_api_wrapper.c."""
+    import subprocess
+
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "c_api_wrapper")
+    libdir = os.path.dirname(pkg.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                           os.path.join(HERE, "c_api_wrapper.c"), "-o", exe, "-L", libdir, "-ldlaf_b200",
+                           f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert "ctx_ok 1 desc 300 300 64 64 ld 300 grid 1x1 rank 0,0 local 300x300" in out.stdout
+    assert "symbols 1" in out.stdout

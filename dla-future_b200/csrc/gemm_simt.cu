@@ -7,6 +7,7 @@
 // Replaces, for s/c/z: cublas{S,C,Z}gemm / {Ssyrk,Cherk,Zherk} / {S,C,Z}trsm tile calls of the reference
 // (include/dlaf/blas/tile.h:249-349).
 #include <cstdint>
+#include <cstdlib>
 
 #include "common.h"
 #include "gemm_args.h"
@@ -141,9 +142,16 @@ template <>
 void launch_gemm_nt<float2>(const GemmArgsT<float2>& a, cudaStream_t s) {
   launch_simt<float2>(a, s);
 }
+void launch_gemm_nt_z_dmma(const GemmArgsT<double2>& a, cudaStream_t stream);  // gemm_zdmma.cu
+
 template <>
 void launch_gemm_nt<double2>(const GemmArgsT<double2>& a, cudaStream_t s) {
-  launch_simt<double2>(a, s);
+  // DLAF_B200_Z_SIMT=1 keeps the first (SIMT) kernel for A/B measurements
+  static const bool simt = std::getenv("DLAF_B200_Z_SIMT") != nullptr;
+  if (simt)
+    launch_simt<double2>(a, s);
+  else
+    launch_gemm_nt_z_dmma(a, s);
 }
 
 }  // namespace dlaf_b200

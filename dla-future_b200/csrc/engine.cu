@@ -3,6 +3,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 #include "comm.h"
 #include "common.h"
@@ -60,6 +61,13 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
   DLAF_CUDA_CHECK(cudaMalloc(&d_info_, sizeof(int)));
   DLAF_CUDA_CHECK(cudaMallocHost(&h_info_, sizeof(int)));
   *h_info_ = 0;
+  if constexpr (std::is_same_v<T, float>) {
+    // DLAF_B200_S_SIMT=1 keeps the SIMT fp32 kernel everywhere (A/B measurements)
+    use_tf32_ = geo_.P * geo_.Q == 1 && nt_ > 1 && std::getenv("DLAF_B200_S_SIMT") == nullptr;
+    if (use_tf32_)
+      for (int i = 0; i < 2; ++i)
+        split_[i].allocate(static_cast<long>(ltr_) * nbp_, nbp_);
+  }
 }
 
 template <class T>
@@ -92,6 +100,10 @@ PotrfEngine<T>::~PotrfEngine() {
     cudaStreamDestroy(sOut_);
   for (auto e : prof_ev_)
     cudaEventDestroy(e);
+  if constexpr (std::is_same_v<T, float>) {
+    for (int i = 0; i < 2; ++i)
+      split_[i].release();
+  }
   cudaFree(own_slab_);
   cudaFree(d_info_);
   cudaFreeHost(h_info_);
@@ -325,6 +337,12 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       if (wait_column)  // rows of block column k below the diagonal tile: updated on stream M
         DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evC_[(k - 1) % 2], 0));
       trsm_panel(tile_ptr(li1, lkc), ld_, mt * nbp_, tkk, ldt, w, sH_);
+      if constexpr (std::is_same_v<T, float>) {
+        if (use_tf32_ && k < nt_ - 1) {
+          split_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sH_);
+          ++launches_;
+        }
+      }
     }
   }
 
@@ -425,6 +443,15 @@ void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows
     const double cplx = (sizeof(T) == 2 * sizeof(base_t<T>)) ? 4.0 : 1.0;
     last_update_flops_ += tiles * cplx * static_cast<double>(nbp_) * nbp_ * nbp_;
   }
+  if constexpr (std::is_same_v<T, float>) {
+    if (use_tf32_) {
+      // 1 x 1 grid: panel row index = local tile row - li1, transposed panel row = tile column - li1
+      launch_gemm_tf32x3(a, split_[slot], static_cast<long>(ri0 - li1) * nbp_, split_[slot],
+                         static_cast<long>(cj0 - li1) * nbp_, st);
+      ++launches_;
+      return;
+    }
+  }
   gemm(a, st);
 }
 
@@ -489,8 +516,8 @@ int PotrfEngine<T>::chunk_of(int lj) const {
 template <class T>
 void PotrfEngine<T>::wait_bulk(int k, int lj, cudaStream_t st) {
   const int nc = nchunks();
-  if (geo_.P * geo_.Q > 1 || lj < 0) {
-    // distributed: the panel workspaces of step k are shared by all chunks -> wait for all of them
+  if (geo_.P * geo_.Q > 1 || lj < 0 || use_tf32_) {
+    // distributed / split panels: the panel workspaces of step k are shared by all chunks -> wait for all
     for (int c = 0; c < nc; ++c)
       DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[2 * c + k % 2], 0));
   }

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "gemm_args.h"
+#include "gemm_tf32.h"
 #include "layout.cuh"
 #include "potrf_tile.cuh"
 #include "types.h"
@@ -142,6 +143,10 @@ private:
   int chunk_of(int lj) const;
   int nchunks() const { return in_end_.empty() ? 1 : static_cast<int>(in_end_.size()); }
   void wait_bulk(int k, int lj, cudaStream_t st);  // bulk of step k done on the chunk of column lj (or on all)
+  // fp32 only: tcgen05 3xTF32 trailing update (gemm_tf32_tcgen05.cu) — the panel of step k is split into
+  // K-major hi/lo parts right after its TRSM (two round-robin slots like the panel workspaces)
+  bool use_tf32_ = false;
+  Tf32Split split_[2];
   int* d_info_ = nullptr;
   int* h_info_ = nullptr;
   long launches_ = 0;

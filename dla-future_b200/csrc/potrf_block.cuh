@@ -8,12 +8,14 @@
 // 16 x 16 grid owns the BS x BS sub-block rows ti*BS.., columns tj*BS.. (BS = G/16).
 // Per panel step J (BS columns at a time):
 //   A1  owners of block column J publish it to shared memory (k-major, padded per row block)
-//   A2  one thread per row: every thread re-derives the Cholesky of the BS x BS pivot block D in
-//       registers (redundantly — cheaper than a barrier per column), then solves its own panel row
-//       x <- x L_D^-H; the BS pivot rows instead receive L_D and X_D = inv(L_D)^H
+//   A2  one thread per row solves its own panel row x <- x L_D^-H against the factor of the BS x BS pivot
+//       block D (in shared memory); the BS pivot rows instead receive L_D and X_D = inv(L_D)^H
 //   B   every thread applies the rank-BS update to its register block:
 //         S(r,s) -= sum_k P(r,k) conj(P(s,k))   for block columns right of J, rows r >= s or r < J*BS
-//       and the pivot block row gets the freshly created X entries  -(X_D-weighted combination).
+//       and the pivot block row gets the freshly created X entries  -(X_D-weighted combination);
+//       the ONE thread owning the next pivot block then factorises it (a latency-bound chain of rsqrt and
+//       dependent FMAs) while all the others are still in their update — measured: with every thread
+//       re-deriving the pivot factor inside A2 that chain was 55 % of the kernel time.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -108,13 +110,12 @@ PB_HD void write_panel(const T (&reg)[C::BS][C::BS], T* panel, int ti) {
       panel[b * C::PROW + C::poff(ti * C::BS + a)] = reg[a][b];
 }
 
-// A2 (row r = t % PB; only threads with `active` write). `sync` is called once, after every thread has
-// read the pivot block and its own row and before any row is written back (the pivot rows are part of
-// what the others read): __syncthreads() on the device, a no-op in the host emulation (which feeds
-// each thread a snapshot). Returns 0 or the 1-based in-block column where the pivot failed (identical
-// in every thread because the pivot block is factorised redundantly).
-template <class C, class T, class SyncF>
-PB_HD int factor_panel_row(T* panel, base_t<T>* dd, base_t<T>* dinv, int J, int t, bool active, SyncF sync) {
+// Pivot-block factorization, executed by ONE thread: the owner of the diagonal register block (ti == tj == J)
+// right after that block received its last update — i.e. overlapped with the rank-BS update every other
+// thread is still busy with. Publishes L_D (scaled strictly-lower part), 1/diag and diag^2 to shared memory.
+// Returns 0 or the 1-based in-block column of a non-positive pivot.
+template <class C, class T>
+PB_HD int factor_pivot_block(const T (&reg)[C::BS][C::BS], T* dfL, base_t<T>* dfinv, base_t<T>* dfsq) {
   using R = base_t<T>;
   constexpr int BS = C::BS;
   T Dm[BS][BS];
@@ -122,40 +123,60 @@ PB_HD int factor_panel_row(T* panel, base_t<T>* dd, base_t<T>* dinv, int J, int 
   for (int b = 0; b < BS; ++b)
 #pragma unroll
     for (int a = 0; a < BS; ++a)
-      Dm[a][b] = (a >= b) ? panel[b * C::PROW + C::poff(J * BS + a)] : make_real<T>(0);
-  const int r = t % C::PB, rb = r / BS, rr = r % BS;
-  T x[BS];
-#pragma unroll
-  for (int k = 0; k < BS; ++k)
-    x[k] = panel[k * C::PROW + C::poff(r)];
-  sync();
-  R invd[BS], dsq[BS];
+      Dm[a][b] = (a >= b) ? reg[a][b] : make_real<T>(0);
+  int fail = 0;
 #pragma unroll
   for (int j = 0; j < BS; ++j) {
     const R ajj = re_of(Dm[j][j]);
-    if (!(ajj > R(0)))
-      return j + 1;
-    invd[j] = fast_rsqrt(ajj);
-    dsq[j] = ajj;  // sqrt taken later, only by the row that needs it
+    if (!(ajj > R(0)) && fail == 0)
+      fail = j + 1;
+    const R inv = fast_rsqrt(ajj);
+    dfinv[j] = inv;
+    dfsq[j] = ajj;
 #pragma unroll
-    for (int a = j + 1; a < BS; ++a)
-      Dm[a][j] = scale_r(Dm[a][j], invd[j]);
+    for (int a = j + 1; a < BS; ++a) {
+      Dm[a][j] = scale_r(Dm[a][j], inv);
+      dfL[a * BS + j] = Dm[a][j];
+    }
 #pragma unroll
     for (int s = j + 1; s < BS; ++s)
 #pragma unroll
       for (int a = s; a < BS; ++a)
         Dm[a][s] = sub_mul_conj(Dm[a][s], Dm[a][j], Dm[s][j]);
   }
-  if (!active)
-    return 0;
+  return fail;
+}
+
+// A2 (threads t < PB, one per panel row): x <- x L_D^-H with the pivot factor read from shared memory.
+// Every thread reads and writes only its own row, the pivot factor lives in its own buffer: no barrier
+// inside this phase.
+template <class C, class T>
+PB_HD void solve_panel_row(T* panel, const T* dfL, const base_t<T>* dfinv, const base_t<T>* dfsq, base_t<T>* dd,
+                           base_t<T>* dinv, int J, int t) {
+  using R = base_t<T>;
+  constexpr int BS = C::BS;
+  const int r = t, rb = r / BS, rr = r % BS;
+  T Lm[BS][BS];
+  R invd[BS];
+#pragma unroll
+  for (int a = 0; a < BS; ++a) {
+    invd[a] = dfinv[a];
+#pragma unroll
+    for (int b = 0; b < BS; ++b)
+      Lm[a][b] = (a > b) ? dfL[a * BS + b] : make_real<T>(0);
+  }
+  T x[BS];
   if (rb != J) {
-    // x <- x L_D^-H : Cholesky rows below the pivot block AND inverse rows above it obey the same rule
+#pragma unroll
+    for (int k = 0; k < BS; ++k)
+      x[k] = panel[k * C::PROW + C::poff(r)];
+    // Cholesky rows below the pivot block AND inverse rows above it obey the same rule
 #pragma unroll
     for (int s = 0; s < BS; ++s) {
       T v = x[s];
 #pragma unroll
       for (int j = 0; j < s; ++j)
-        v = sub_mul_conj(v, x[j], Dm[s][j]);
+        v = sub_mul_conj(v, x[j], Lm[s][j]);
       x[s] = scale_r(v, invd[s]);
     }
   }
@@ -178,24 +199,25 @@ PB_HD int factor_panel_row(T* panel, base_t<T>* dd, base_t<T>* dinv, int J, int 
 #pragma unroll
         for (int j = 0; j < BS; ++j)
           if (j >= c && j < s)
-            v = sub_mul(v, Dm[s][j], m[j]);
+            v = sub_mul(v, Lm[s][j], m[j]);
         m[s] = scale_r(v, invd[s]);
       }
     }
-    // (static indices only: a run-time row index would push Dm into local memory)
+    // (static indices only: a run-time row index would push Lm into local memory)
 #pragma unroll
     for (int s = 0; s < BS; ++s) {
+      x[s] = make_real<T>(0);
       if (s > rr)
         x[s] = conj_val(m[s]);
 #pragma unroll
       for (int a = 0; a < BS; ++a)
         if (a == rr && s < a)
-          x[s] = Dm[a][s];
+          x[s] = Lm[a][s];
     }
 #pragma unroll
     for (int s = 0; s < BS; ++s)
       if (s == rr) {
-        const R d = full_sqrt(dsq[s]);
+        const R d = full_sqrt(dfsq[s]);
         x[s] = make_real<T>(d);
         dd[r] = d;
         dinv[r] = invd[s];
@@ -204,7 +226,6 @@ PB_HD int factor_panel_row(T* panel, base_t<T>* dd, base_t<T>* dinv, int J, int 
 #pragma unroll
   for (int k = 0; k < BS; ++k)
     panel[k * C::PROW + C::poff(r)] = x[k];
-  return 0;
 }
 
 // B (all threads)

@@ -177,26 +177,39 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
   T* panel = reinterpret_cast<T*>(smem_raw);
   R* dd = reinterpret_cast<R*>(panel + C::PANEL_ELEMS);
   R* dinv = dd + PB;
-  int* sfail = reinterpret_cast<int*>(dinv + PB);
+  R* dfinv = dinv + PB;  // pivot-block factor: 1/diag, diag^2, strictly lower part
+  R* dfsq = dfinv + BS;
+  T* dfL = reinterpret_cast<T*>(dfsq + BS);
+  int* sfail = reinterpret_cast<int*>(dfL + BS * BS);
   const int tid = threadIdx.x, ti = tid % 16, tj = tid / 16;
 
   T reg[BS][BS];
   pblock::load_block<C, T>(reg, Tm, ldt, ti, tj);
   if (tid == 0)
     *sfail = 0;
+  __syncthreads();
+  if (ti == 0 && tj == 0) {
+    const int f = pblock::factor_pivot_block<C, T>(reg, dfL, dfinv, dfsq);
+    if (f)
+      *sfail = f;
+  }
   int fail = 0;
   for (int J = 0; J < 16; ++J) {
     if (tj == J)
       pblock::write_panel<C, T>(reg, panel, ti);
-    __syncthreads();
-    const int f = pblock::factor_panel_row<C, T>(panel, dd, dinv, J, tid, tid < PB, [] { __syncthreads(); });
-    if (f && tid == 0)
-      *sfail = J * BS + f;
-    __syncthreads();
+    __syncthreads();  // panel J and the factor of its pivot block are published
     fail = *sfail;
     if (fail)
       break;
+    if (tid < PB)
+      pblock::solve_panel_row<C, T>(panel, dfL, dfinv, dfsq, dd, dinv, J, tid);
+    __syncthreads();
     pblock::update_block<C, T>(reg, panel, dinv, J, ti, tj);
+    if (J + 1 < 16 && ti == J + 1 && tj == J + 1) {
+      const int f = pblock::factor_pivot_block<C, T>(reg, dfL, dfinv, dfsq);
+      if (f)
+        *sfail = (J + 1) * BS + f;
+    }
     __syncthreads();
   }
   if (fail) {
@@ -213,7 +226,7 @@ template <class T>
 void launch_blocked(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
   constexpr int PB = Gran<T>::value;
   using C = pblock::Cfg<T, PB>;
-  constexpr int smem = C::PANEL_ELEMS * sizeof(T) + 2 * PB * sizeof(base_t<T>) + 16;
+  constexpr int smem = C::PANEL_ELEMS * sizeof(T) + (2 * PB + 2 * C::BS) * sizeof(base_t<T>) + C::BS * C::BS * sizeof(T) + 16;
   potrf_inv_blocked_kernel<T, PB><<<1, kPotrfThreads, smem, stream>>>(t, ldt, w, ldw, info, info_offset);
   DLAF_CUDA_CHECK(cudaGetLastError());
 }

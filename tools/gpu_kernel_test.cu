@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -12,6 +14,7 @@
 #include "../dla-future_b200/csrc/common.h"
 #include "../dla-future_b200/csrc/gemm_dmma.cuh"
 #include "../dla-future_b200/csrc/potrf_tile.cuh"
+#include "../dla-future_b200/csrc/gemm_tf32.h"
 
 using namespace dlaf_b200;
 
@@ -293,6 +296,71 @@ int main() {
       cudaFree(a); cudaFree(b); cudaFree(c);
     }
     cublasDestroy(h);
+  }
+  // ---- tcgen05 3xTF32 GEMM (fp32)
+  if (std::getenv("SKIP_TF32") == nullptr) {
+    std::mt19937_64 rng2(7);
+    std::uniform_real_distribution<float> df(-1.f, 1.f);
+    for (int mode = 0; mode < 2; ++mode) {
+      const int M = 384, N = 256, K = 96;
+      const long lda = M + 4, ldc = M + 8;
+      std::vector<float> P(lda * K), C(ldc * N), R(ldc * N);
+      for (auto& x : P) x = df(rng2);
+      for (auto& x : C) x = df(rng2);
+      float *dP, *dC;
+      cudaMalloc(&dP, P.size() * 4); cudaMalloc(&dC, C.size() * 4);
+      cudaMemcpy(dP, P.data(), P.size() * 4, cudaMemcpyHostToDevice);
+      cudaMemcpy(dC, C.data(), C.size() * 4, cudaMemcpyHostToDevice);
+      Tf32Split sp; sp.allocate(M, K);
+      sp.split(dP, lda, M, 0);
+      GemmArgsT<float> g{};
+      g.C = dC; g.ldc = ldc; g.M = M; g.N = N; g.K = K; g.alpha = -1.0; g.beta = 1.0;
+      g.mask = mode ? kMaskLower : kMaskNone; g.nbp = 128; g.P = g.Q = 1;
+      launch_gemm_tf32x3(g, sp, 0, sp, 0, 0);   // C -= P[0:M] * P[0:N]^T
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { std::printf("tf32x3 gemm FAILED: %s\n", cudaGetErrorString(e)); return 1; }
+      cudaMemcpy(R.data(), dC, C.size() * 4, cudaMemcpyDeviceToHost);
+      double maxerr = 0, e1 = 0, e2a = 0, e2b = 0, e3 = 0; long wrong = 0;
+      auto trunc = [](float v) { uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+      for (int j = 0; j < N; ++j) for (int i = 0; i < M; ++i) {
+        const bool active = !mode || i >= j;
+        if (active) {
+          double s = 0, s1 = 0, s2a = 0, s2b = 0, s3 = 0;
+          for (int k = 0; k < K; ++k) {
+            const float a = P[i + k * lda], b = P[j + k * lda];
+            const float ah = trunc(a), al = trunc(a - ah), bh = trunc(b), bl = trunc(b - bh);
+            s += (double)a * b; s1 += (double)ah * bh; s2a += (double)ah * bh + (double)ah * bl; s2b += (double)ah * bh + (double)al * bh;
+            s3 += (double)ah * bh + (double)ah * bl + (double)al * bh;
+          }
+          const double got = (double)C[i + j * ldc] - (double)R[i + j * ldc];  // = computed product
+          maxerr = std::fmax(maxerr, std::fabs(got - s)); e1 = std::fmax(e1, std::fabs(got - s1));
+          e2a = std::fmax(e2a, std::fabs(got - s2a)); e2b = std::fmax(e2b, std::fabs(got - s2b)); e3 = std::fmax(e3, std::fabs(got - s3));
+        } else if (R[i + j * ldc] != C[i + j * ldc]) wrong++;
+      }
+      std::printf("tf32x3 tcgen05 GEMM mode %d: max err vs exact %.3e | vs hi*hi %.3e | vs +hi*lo %.3e | vs +lo*hi %.3e | vs all three %.3e ; masked modified %ld\n", mode, maxerr, e1, e2a, e2b, e3, wrong);
+      sp.release(); cudaFree(dP); cudaFree(dC);
+    }
+    {
+      cublasHandle_t h; cublasCreate(&h);
+      const int M = 16384, K = 1024;
+      float *dP, *dC; cudaMalloc(&dP, (size_t)M * K * 4); cudaMalloc(&dC, (size_t)M * M * 4);
+      cudaMemset(dP, 0, (size_t)M * K * 4); cudaMemset(dC, 0, (size_t)M * M * 4);
+      Tf32Split sp; sp.allocate(M, K); sp.split(dP, M, M, 0);
+      GemmArgsT<float> g{}; g.C = dC; g.ldc = M; g.M = M; g.N = M; g.K = K; g.alpha = -1; g.beta = 1; g.mask = kMaskNone; g.nbp = 1024; g.P = g.Q = 1;
+      launch_gemm_tf32x3(g, sp, 0, sp, 0, 0); cudaDeviceSynchronize();
+      cudaEventRecord(e0); for (int i = 0; i < 3; ++i) launch_gemm_tf32x3(g, sp, 0, sp, 0, 0); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      double ms = time_ms(e0, e1) / 3; double fl = 2.0 * M * (double)M * K;
+      std::printf("tf32x3 tcgen05 %dx%dx%d: %.3f ms  %.1f TFLOP/s (fp32-equivalent; %.1f TF/s of TF32 MMAs)\n", M, M, K, ms, fl / ms / 1e9, 3 * fl / ms / 1e9);
+      const float al = -1, be = 1;
+      cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, M, M, K, &al, dP, M, dP, M, &be, dC, M);
+      cudaEventRecord(e0); for (int i = 0; i < 3; ++i) cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, M, M, K, &al, dP, M, dP, M, &be, dC, M); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      ms = time_ms(e0, e1) / 3; std::printf("cublasSgemm (fp32)       : %.3f ms  %.1f TFLOP/s\n", ms, fl / ms / 1e9);
+      cublasSetMathMode(h, CUBLAS_TF32_TENSOR_OP_MATH);
+      cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, M, M, K, &al, dP, M, dP, M, &be, dC, M);
+      cudaEventRecord(e0); for (int i = 0; i < 3; ++i) cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, M, M, K, &al, dP, M, dP, M, &be, dC, M); cudaEventRecord(e1); cudaEventSynchronize(e1);
+      ms = time_ms(e0, e1) / 3; std::printf("cublasSgemm (1xTF32 mode): %.3f ms  %.1f TFLOP/s\n", ms, fl / ms / 1e9);
+      sp.release(); cudaFree(dP); cudaFree(dC); cublasDestroy(h);
+    }
   }
   std::printf("done\n");
   return 0;

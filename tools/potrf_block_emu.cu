@@ -60,19 +60,20 @@ int run(const char* name, bool make_fail) {
   static T reg[256][C::BS][C::BS];
   for (int tid = 0; tid < 256; ++tid) load_block<C, T>(reg[tid], Tm.data(), ld, tid % 16, tid / 16);
   int fail = 0;
+  std::vector<T> dfL(BS * BS);
+  std::vector<R> dfinv(BS), dfsq(BS);
+  {
+    int f = factor_pivot_block<C, T>(reg[0], dfL.data(), dfinv.data(), dfsq.data());
+    if (f) fail = f;
+  }
   for (int J = 0; J < 16 && !fail; ++J) {
     for (int tid = 0; tid < 256; ++tid) if (tid / 16 == J) write_panel<C, T>(reg[tid], panel.data(), tid % 16);
-    // A2 reads the whole pivot block before any row is written back -> emulate with a snapshot for D
-    std::vector<T> snap = panel;
-    for (int t = 0; t < n; ++t) {
-      // each thread reads D and its own row from the pre-A2 panel, writes only its own row
-      std::vector<T> work = snap;
-      int f = factor_panel_row<C, T>(work.data(), dd.data(), dinv.data(), J, t, true, [] {});
-      if (f) { fail = J * BS + f; break; }
-      for (int k = 0; k < BS; ++k) panel[k * C::PROW + C::poff(t)] = work[k * C::PROW + C::poff(t)];
-    }
-    if (fail) break;
+    for (int t = 0; t < n; ++t) solve_panel_row<C, T>(panel.data(), dfL.data(), dfinv.data(), dfsq.data(), dd.data(), dinv.data(), J, t);
     for (int tid = 0; tid < 256; ++tid) update_block<C, T>(reg[tid], panel.data(), dinv.data(), J, tid % 16, tid / 16);
+    if (J + 1 < 16) {
+      int f = factor_pivot_block<C, T>(reg[(J + 1) * 16 + (J + 1)], dfL.data(), dfinv.data(), dfsq.data());
+      if (f) fail = (J + 1) * BS + f;
+    }
   }
   if (make_fail || ref_fail) {
     std::printf("%-8s fail test: kernel %d reference %d %s\n", name, fail, ref_fail, fail == ref_fail ? "OK" : "MISMATCH");

@@ -151,8 +151,8 @@ PB_HD int factor_pivot_block(const T (&reg)[C::BS][C::BS], T* dfL, base_t<T>* df
 // Every thread reads and writes only its own row, the pivot factor lives in its own buffer: no barrier
 // inside this phase.
 template <class C, class T>
-PB_HD void solve_panel_row(T* panel, const T* dfL, const base_t<T>* dfinv, const base_t<T>* dfsq, base_t<T>* dd,
-                           base_t<T>* dinv, int J, int t) {
+PB_HD void solve_panel_row(T* panel, const T* dfL, const base_t<T>* dfinv, const base_t<T>* dfsq, T* msc,
+                           base_t<T>* dd, base_t<T>* dinv, int J, int t) {
   using R = base_t<T>;
   constexpr int BS = C::BS;
   const int r = t, rb = r / BS, rr = r % BS;
@@ -181,47 +181,46 @@ PB_HD void solve_panel_row(T* panel, const T* dfL, const base_t<T>* dfinv, const
     }
   }
   else {
-    // pivot row rr: [ L_D(rr, 0..rr-1) | diag | X_D(rr, s) = conj(M_D(s, rr)), s > rr ],  M_D = inv(L_D)
-    T m[BS];
-#pragma unroll
-    for (int s = 0; s < BS; ++s)
-      m[s] = make_real<T>(0);
+    // pivot row rr: [ L_D(rr, 0..rr-1) | diag | X_D(rr, s) = conj(M_D(s, rr)), s > rr ],  M_D = inv(L_D).
+    // All BS columns of M_D in registers with compile-time indices: the columns are independent chains, so
+    // the FP64 pipe latency (8 clk per dependent op) is hidden by instruction-level parallelism across them;
+    // a run-time-bounded loop over shared memory for the single needed column measured ~3k clk per step.
+    (void) msc;
+    T M[BS][BS];
 #pragma unroll
     for (int c = 0; c < BS; ++c) {
-      if (c != rr)
-        continue;
-      m[c] = make_real<T>(invd[c]);
+      M[c][c] = make_real<T>(invd[c]);
 #pragma unroll
-      for (int s = 0; s < BS; ++s) {
-        if (s <= c)
-          continue;
+      for (int s = c + 1; s < BS; ++s) {
         T v = make_real<T>(0);
 #pragma unroll
-        for (int j = 0; j < BS; ++j)
-          if (j >= c && j < s)
-            v = sub_mul(v, Lm[s][j], m[j]);
-        m[s] = scale_r(v, invd[s]);
+        for (int j = c; j < s; ++j)
+          v = sub_mul(v, Lm[s][j], M[j][c]);
+        M[s][c] = scale_r(v, invd[s]);
       }
     }
-    // (static indices only: a run-time row index would push Lm into local memory)
+    R dsel = R(0), isel = R(0);
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+      if (a == rr) {
+        dsel = dfsq[a];
+        isel = invd[a];
+      }
+    const R d = full_sqrt(dsel);
 #pragma unroll
     for (int s = 0; s < BS; ++s) {
-      x[s] = make_real<T>(0);
-      if (s > rr)
-        x[s] = conj_val(m[s]);
+      T v = make_real<T>(0);
 #pragma unroll
-      for (int a = 0; a < BS; ++a)
+      for (int a = 0; a < BS; ++a) {
         if (a == rr && s < a)
-          x[s] = Lm[a][s];
-    }
-#pragma unroll
-    for (int s = 0; s < BS; ++s)
-      if (s == rr) {
-        const R d = full_sqrt(dfsq[s]);
-        x[s] = make_real<T>(d);
-        dd[r] = d;
-        dinv[r] = invd[s];
+          v = Lm[a][s];              // L_D(rr, s)
+        if (a == rr && s > a)
+          v = conj_val(M[s][a]);     // X_D(rr, s) = conj(M_D(s, rr))
       }
+      x[s] = (s == rr) ? make_real<T>(d) : v;
+    }
+    dd[r] = d;
+    dinv[r] = isel;
   }
 #pragma unroll
   for (int k = 0; k < BS; ++k)
@@ -248,42 +247,24 @@ PB_HD void update_block(T (&reg)[C::BS][C::BS], const T* panel, const base_t<T>*
   const bool piv = (ti == J);
   if (!(full || diag || piv))
     return;  // rows strictly between the pivot block and the column's own diagonal block: still zero
-  if (piv) {
-    R dv[BS];
+  // One code path for all three cases (every warp holds a lane of each kind, a branch here would make every
+  // warp execute the update twice). The pivot block row (ti == J) receives the freshly created
+  //   X(r,s) = -( sum_{k>a} X_D(a,k) conj(P(s,k)) + dinv_a conj(P(s,a)) ),
+  // which is the general rank-BS update applied to a zero block with the row operand patched:
+  //   rk'[a] = X_D(a,k) for k > a,  dinv_a for k == a,  0 for k < a   (its registers are still zero).
+  R dv[BS];
 #pragma unroll
-    for (int a = 0; a < BS; ++a) {
-      dv[a] = dinv[J * BS + a];
-#pragma unroll
-      for (int b = 0; b < BS; ++b)
-        reg[a][b] = make_real<T>(0);
-    }
-#pragma unroll
-    for (int k = 0; k < BS; ++k) {
-      T rk[BS], ck[BS];
-#pragma unroll
-      for (int a = 0; a < BS; ++a)
-        rk[a] = panel[k * C::PROW + C::poff(ti * BS + a)];
-#pragma unroll
-      for (int b = 0; b < BS; ++b)
-        ck[b] = panel[k * C::PROW + C::poff(tj * BS + b)];
-#pragma unroll
-      for (int a = 0; a < BS; ++a) {
-        if (k < a)
-          continue;
-        const T coef = (k == a) ? make_real<T>(dv[a]) : rk[a];
-#pragma unroll
-        for (int b = 0; b < BS; ++b)
-          reg[a][b] = sub_mul_conj(reg[a][b], coef, ck[b]);
-      }
-    }
-    return;
-  }
+  for (int a = 0; a < BS; ++a)
+    dv[a] = piv ? dinv[J * BS + a] : R(0);
 #pragma unroll
   for (int k = 0; k < BS; ++k) {
     T rk[BS], ck[BS];
 #pragma unroll
-    for (int a = 0; a < BS; ++a)
+    for (int a = 0; a < BS; ++a) {
       rk[a] = panel[k * C::PROW + C::poff(ti * BS + a)];
+      if (piv)
+        rk[a] = (k > a) ? rk[a] : (k == a ? make_real<T>(dv[a]) : make_real<T>(0));
+    }
 #pragma unroll
     for (int b = 0; b < BS; ++b)
       ck[b] = panel[k * C::PROW + C::poff(tj * BS + b)];

@@ -165,6 +165,14 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
   }
 }
 
+// Measurement aid: when non-null, thread 0 and the last thread record clock64() at every phase boundary.
+__device__ long long* g_potrf_clock_trace = nullptr;
+#define POTRF_TRACE(slot)                                                            \
+  do {                                                                               \
+    if (trace && (tid == 0 || tid == kPotrfThreads - 1))                              \
+      trace[((J) * 8 + (slot)) * 2 + (tid != 0)] = clock64();                        \
+  } while (0)
+
 // ---- the blocked, register-resident kernel (potrf_block.cuh) -------------------------------------
 template <class T, int PB>
 __global__ void __launch_bounds__(kPotrfThreads, 1)
@@ -180,7 +188,8 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
   R* dfinv = dinv + PB;  // pivot-block factor: 1/diag, diag^2, strictly lower part
   R* dfsq = dfinv + BS;
   T* dfL = reinterpret_cast<T*>(dfsq + BS);
-  int* sfail = reinterpret_cast<int*>(dfL + BS * BS);
+  T* msc = dfL + BS * BS;  // scratch: columns of inv(L_D) under construction
+  int* sfail = reinterpret_cast<int*>(msc + BS * BS);
   const int tid = threadIdx.x, ti = tid % 16, tj = tid / 16;
 
   T reg[BS][BS];
@@ -194,23 +203,32 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
       *sfail = f;
   }
   int fail = 0;
+  long long* trace = g_potrf_clock_trace;
   for (int J = 0; J < 16; ++J) {
+    POTRF_TRACE(0);
     if (tj == J)
       pblock::write_panel<C, T>(reg, panel, ti);
+    POTRF_TRACE(1);
     __syncthreads();  // panel J and the factor of its pivot block are published
+    POTRF_TRACE(2);
     fail = *sfail;
     if (fail)
       break;
     if (tid < PB)
-      pblock::solve_panel_row<C, T>(panel, dfL, dfinv, dfsq, dd, dinv, J, tid);
+      pblock::solve_panel_row<C, T>(panel, dfL, dfinv, dfsq, msc, dd, dinv, J, tid);
+    POTRF_TRACE(3);
     __syncthreads();
+    POTRF_TRACE(4);
     pblock::update_block<C, T>(reg, panel, dinv, J, ti, tj);
+    POTRF_TRACE(5);
     if (J + 1 < 16 && ti == J + 1 && tj == J + 1) {
       const int f = pblock::factor_pivot_block<C, T>(reg, dfL, dfinv, dfsq);
       if (f)
         *sfail = (J + 1) * BS + f;
     }
+    POTRF_TRACE(6);
     __syncthreads();
+    POTRF_TRACE(7);
   }
   if (fail) {
     if (tid == 0)
@@ -226,7 +244,7 @@ template <class T>
 void launch_blocked(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
   constexpr int PB = Gran<T>::value;
   using C = pblock::Cfg<T, PB>;
-  constexpr int smem = C::PANEL_ELEMS * sizeof(T) + (2 * PB + 2 * C::BS) * sizeof(base_t<T>) + C::BS * C::BS * sizeof(T) + 16;
+  constexpr int smem = C::PANEL_ELEMS * sizeof(T) + (2 * PB + 2 * C::BS) * sizeof(base_t<T>) + 2 * C::BS * C::BS * sizeof(T) + 16;
   potrf_inv_blocked_kernel<T, PB><<<1, kPotrfThreads, smem, stream>>>(t, ldt, w, ldw, info, info_offset);
   DLAF_CUDA_CHECK(cudaGetLastError());
 }
@@ -254,6 +272,10 @@ void launch_impl(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cud
 }
 
 }  // namespace
+
+void potrf_set_clock_trace(long long* dev_buffer) {
+  DLAF_CUDA_CHECK(cudaMemcpyToSymbol(g_potrf_clock_trace, &dev_buffer, sizeof(dev_buffer)));
+}
 
 void launch_potrf128_inv_f64(double* T, long ldt, double* W, long ldw, int* info, int info_offset,
                              cudaStream_t stream) {

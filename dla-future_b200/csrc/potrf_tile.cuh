@@ -25,6 +25,9 @@ constexpr int kPotrfBlock = 128;
 void launch_potrf128_inv_f64(double* T, long ldt, double* W, long ldw, int* info, int info_offset,
                              cudaStream_t stream);
 
+// Measurement aid (tools/): device buffer of 16*8*2 clock64 stamps per launch, nullptr switches it off.
+void potrf_set_clock_trace(long long* dev_buffer);
+
 // Per element type entry point: Cholesky + inverse of one Gran<T> x Gran<T> diagonal block.
 template <class T>
 void launch_potrf_inv(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream);

@@ -212,6 +212,32 @@ int main() {
     cudaDeviceSynchronize();
     cudaMemcpy(&info, dinfo, 4, cudaMemcpyDeviceToHost);
     std::printf("potrf128 zero matrix: info %d (expect 1)\n", info);
+    // per-phase clock trace (thread 0 and thread 255)
+    {
+      cudaMemcpy(dT, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
+      long long* dtr; cudaMalloc(&dtr, 16 * 8 * 2 * 8); cudaMemset(dtr, 0, 16 * 8 * 2 * 8);
+      potrf_set_clock_trace(dtr);
+      launch_potrf128_inv_f64(dT, ld, dW, n, dinfo, 0, 0);
+      cudaDeviceSynchronize();
+      potrf_set_clock_trace(nullptr);
+      std::vector<long long> tr(16 * 8 * 2); cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost);
+      const char* names[7] = {"write_panel", "bar1", "solve", "bar2", "update", "factor", "bar3"};
+      for (int th = 0; th < 2; ++th) {
+        long long sum[7] = {0};
+        for (int J = 0; J < 16; ++J) for (int q = 0; q < 7; ++q) sum[q] += tr[(J * 8 + q + 1) * 2 + th] - tr[(J * 8 + q) * 2 + th];
+        std::printf("potrf128 phase clocks thread %3d (sum over 16 steps):", th ? 255 : 0);
+        for (int q = 0; q < 7; ++q) std::printf(" %s %lld", names[q], sum[q]);
+        std::printf(" | total %lld\n", tr[(15 * 8 + 7) * 2 + th] - tr[th]);
+      }
+      for (int J : {0, 4, 8, 12, 15}) {
+        std::printf("  step %2d thread0:", J);
+        for (int q = 0; q < 7; ++q) std::printf(" %lld", tr[(J * 8 + q + 1) * 2] - tr[(J * 8 + q) * 2]);
+        std::printf("   thread255:");
+        for (int q = 0; q < 7; ++q) std::printf(" %lld", tr[(J * 8 + q + 1) * 2 + 1] - tr[(J * 8 + q) * 2 + 1]);
+        std::printf("\n");
+      }
+      cudaFree(dtr);
+    }
     // timing
     cudaMemcpy(dT, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
     cudaMemset(dinfo, 0, 4);

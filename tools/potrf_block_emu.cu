@@ -60,7 +60,7 @@ int run(const char* name, bool make_fail) {
   static T reg[256][C::BS][C::BS];
   for (int tid = 0; tid < 256; ++tid) load_block<C, T>(reg[tid], Tm.data(), ld, tid % 16, tid / 16);
   int fail = 0;
-  std::vector<T> dfL(BS * BS);
+  std::vector<T> dfL(BS * BS), msc(BS * BS);
   std::vector<R> dfinv(BS), dfsq(BS);
   {
     int f = factor_pivot_block<C, T>(reg[0], dfL.data(), dfinv.data(), dfsq.data());
@@ -68,7 +68,7 @@ int run(const char* name, bool make_fail) {
   }
   for (int J = 0; J < 16 && !fail; ++J) {
     for (int tid = 0; tid < 256; ++tid) if (tid / 16 == J) write_panel<C, T>(reg[tid], panel.data(), tid % 16);
-    for (int t = 0; t < n; ++t) solve_panel_row<C, T>(panel.data(), dfL.data(), dfinv.data(), dfsq.data(), dd.data(), dinv.data(), J, t);
+    for (int t = 0; t < n; ++t) solve_panel_row<C, T>(panel.data(), dfL.data(), dfinv.data(), dfsq.data(), msc.data(), dd.data(), dinv.data(), J, t);
     for (int tid = 0; tid < 256; ++tid) update_block<C, T>(reg[tid], panel.data(), dinv.data(), J, tid % 16, tid / 16);
     if (J + 1 < 16) {
       int f = factor_pivot_block<C, T>(reg[(J + 1) * 16 + (J + 1)], dfL.data(), dfinv.data(), dfsq.data());

@@ -244,6 +244,7 @@ def run_ours(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     prof_ms = prof_fl = 0.0
     prof_n = 0
+    chain = None
     launches = 0
     for i in range(W):
         d_work.copy_(d_ref)
@@ -262,6 +263,7 @@ def run_ours(args):
             ev[i][1].record(stream)
             info = pkg.wait(ctx, stream.cuda_stream)
             assert info == 0, f"info {info}"
+            chain = pkg.read_chain_profile(ctx)
             ms, fl, cnt = pkg.read_profile(ctx)
             prof_ms += ms
             prof_fl += fl
@@ -292,7 +294,7 @@ def run_ours(args):
         "traffic": None,
         "peak_source": "measured now on this GPU: DMMA.8x8x4 issue-rate microbenchmark (dlaf_b200_measure_fp64_tensor_peak_tflops); "
                        "MEASURED_PEAKS.json holds no fp64 figure (bf16 cuBLAS + HBM copy only); nominal B200 fp64 = 40 TFLOP/s",
-        "launches_timed": prof_n, "kernel_ms_per_step": prof_ms / K if K else None,
+        "launches_timed": prof_n, "critical_path_ms_last_step": chain, "kernel_ms_per_step": prof_ms / K if K else None,
         "kernel_share_of_step": (prof_ms / K) / ms_per_step if K else None,
         "whole_potrf_frac_of_peak": value / 1e3 / (peak * world),
     }

@@ -34,7 +34,7 @@ C_API_SYMBOLS = [
     *[f"dlaf_b200_set_random_hermitian_positive_definite_{t}" for t in "sdcz"],
     *[f"dlaf_b200_check_cholesky_{t}" for t in "sdcz"], "dlaf_b200_grid_barrier",
     "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info",
-    "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops",
+    "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
 ]
 
@@ -141,6 +141,8 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_set_profiling.restype = None
     L.dlaf_b200_read_profile.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     L.dlaf_b200_read_profile.restype = None
+    L.dlaf_b200_read_chain_profile.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
+    L.dlaf_b200_read_chain_profile.restype = None
     L.dlaf_b200_measure_fp64_tensor_peak_tflops.restype = ctypes.c_double
     L.dlaf_b200_grid_info.argtypes = [ci, ctypes.POINTER(ci)]
     L.dlaf_b200_grid_info.restype = None
@@ -272,6 +274,16 @@ def read_profile(ctx: int):
     out = (ctypes.c_double * 3)()
     lib().dlaf_b200_read_profile(ctx, out)
     return out[0], out[1], int(out[2])
+
+
+def read_chain_profile(ctx: int):
+    """Critical-path breakdown (ms, summed over steps): dict of the five phases + number of steps."""
+    out = (ctypes.c_double * 6)()
+    lib().dlaf_b200_read_chain_profile(ctx, out)
+    keys = ["wait_bulk_and_diag_update", "diag_tile_potrf", "diag_bcast", "wait_column_and_trsm", "panel_pack_and_bcasts"]
+    d = {k: out[i] for i, k in enumerate(keys)}
+    d["steps"] = int(out[5])
+    return d
 
 
 def measure_fp64_tensor_peak_tflops() -> float:

@@ -40,6 +40,7 @@ struct EngineSlotBase {
   virtual long launches() const = 0;
   virtual void set_profiling(bool on) = 0;
   virtual void read_profile(double out[3]) = 0;
+  virtual void read_chain_profile(double out[6]) = 0;
 };
 
 template <class D>
@@ -59,6 +60,12 @@ struct EngineSlot : EngineSlotBase {
     out[0] = out[1] = out[2] = 0;
     if (eng)
       eng->read_profile(out);
+  }
+  void read_chain_profile(double out[6]) override {
+    for (int i = 0; i < 6; ++i)
+      out[i] = 0;
+    if (eng)
+      eng->read_chain_profile(out);
   }
   D* ensure_stage(size_t elems) {
     if (elems > stage_elems) {
@@ -565,6 +572,14 @@ void dlaf_b200_read_profile(int ctx, double out[3]) noexcept {
   out[0] = out[1] = out[2] = 0;
   if (c.last_type >= 0 && c.slot[c.last_type])
     c.slot[c.last_type]->read_profile(out);
+}
+
+void dlaf_b200_read_chain_profile(int ctx, double out[6]) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  for (int i = 0; i < 6; ++i)
+    out[i] = 0;
+  if (c.last_type >= 0 && c.slot[c.last_type])
+    c.slot[c.last_type]->read_chain_profile(out);
 }
 
 void dlaf_b200_grid_info(int ctx, int out[4]) noexcept {

@@ -100,6 +100,8 @@ PotrfEngine<T>::~PotrfEngine() {
     cudaStreamDestroy(sOut_);
   for (auto e : prof_ev_)
     cudaEventDestroy(e);
+  for (auto e : chain_ev_)
+    cudaEventDestroy(e);
   if constexpr (std::is_same_v<T, float>) {
     for (int i = 0; i < 2; ++i)
       split_[i].release();
@@ -307,6 +309,9 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
   const size_t wsz = static_cast<size_t>(ns_) * G * G;
   const int slot = k % 2;
 
+  if (k == 0)
+    chain_stamp(0, 0);
+  chain_stamp(k, 1);
   if (in_col) {
     wait_columns(lkc + 1, sH_);
     const T* tkk = nullptr;
@@ -320,8 +325,10 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
         DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dbuf, sizeof(T) * nbp_, tile, sizeof(T) * ld_, sizeof(T) * nbp_,
                                           nbp_, cudaMemcpyDeviceToDevice, sH_));
       }
+      chain_stamp(k, 2);
       DLAF_NCCL_CHECK(ncclBroadcast(dbuf, dbuf, (tsz + wsz) * NT::mult, NT::value, col_comm_rank(owner_r),
                                     col_comm_, sH_));
+      chain_stamp(k, 3);
       tkk = dbuf;
       ldt = nbp_;
       w = dbuf + tsz;
@@ -332,6 +339,8 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       tkk = tile;
       ldt = ld_;
       w = wbuf_[slot];
+      chain_stamp(k, 2);
+      chain_stamp(k, 3);
     }
     if (mt > 0) {
       if (wait_column)  // rows of block column k below the diagonal tile: updated on stream M
@@ -346,6 +355,11 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
     }
   }
 
+  if (!in_col) {
+    chain_stamp(k, 2);
+    chain_stamp(k, 3);
+  }
+  chain_stamp(k, 4);
   if (k < nt_ - 1 && P * Q > 1) {
     if (mt > 0) {
       if (in_col) {
@@ -371,6 +385,7 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       DLAF_NCCL_CHECK(ncclGroupEnd());
     }
   }
+  chain_stamp(k, 5);
   DLAF_CUDA_CHECK(cudaEventRecord(evP_[slot], sH_));
   if (in_col)
     download_column(lkc, evP_[slot]);  // block column k is final on this rank
@@ -599,6 +614,36 @@ void PotrfEngine<T>::factorize_host(T* host, long ldh, cudaStream_t s) {
 }
 
 template <class T>
+void PotrfEngine<T>::chain_stamp(int k, int which) {
+  if (!profiling_)
+    return;
+  const size_t idx = static_cast<size_t>(k) * 6 + which;
+  while (chain_ev_.size() <= idx) {
+    cudaEvent_t e;
+    DLAF_CUDA_CHECK(cudaEventCreate(&e));
+    chain_ev_.push_back(e);
+  }
+  DLAF_CUDA_CHECK(cudaEventRecord(chain_ev_[idx], sH_));
+  if (chain_used_ < idx + 1)
+    chain_used_ = idx + 1;
+}
+
+template <class T>
+void PotrfEngine<T>::read_chain_profile(double out[6]) {
+  for (int i = 0; i < 6; ++i)
+    out[i] = 0.0;
+  const size_t steps = chain_used_ / 6;
+  for (size_t k = 0; k < steps; ++k) {
+    for (int i = 0; i < 5; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, chain_ev_[k * 6 + i], chain_ev_[k * 6 + i + 1]) == cudaSuccess)
+        out[i] += ms;
+    }
+    out[5] += 1.0;
+  }
+}
+
+template <class T>
 void PotrfEngine<T>::read_profile(double out[3]) {
   out[0] = out[1] = out[2] = 0.0;
   for (size_t i = 0; i < prof_used_; ++i) {
@@ -616,6 +661,7 @@ template <class T>
 void PotrfEngine<T>::factorize(cudaStream_t s) {
   launches_ = 0;
   prof_used_ = 0;
+  chain_used_ = 0;
   if (nt_ == 0)
     return;
   if (!external_)
@@ -708,6 +754,7 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
     update(k, kNextColumnRest, sM_);
     DLAF_CUDA_CHECK(cudaEventRecord(evC_[k % 2], sM_));
     // critical path on stream H: the diagonal tile (k+1,k+1), then P_{k+1} (its TRSM waits for stream M)
+    chain_stamp(k + 1, 0);
     if (k >= 1)
       wait_bulk(k - 1, own_next ? lj1 : -1, sH_);
     update(k, kNextDiag, sH_);

@@ -94,6 +94,10 @@ public:
   void set_profiling(bool on) { profiling_ = on; }
   // out = {sum of launch durations [ms], algorithmic flops of those launches, number of launches}
   void read_profile(double out[3]);
+  // Critical-path breakdown of the last factorize (profiling mode), summed over the steps, in ms:
+  // out = {diag-tile update wait+run, diagonal tile factorization, diag broadcast, wait for column + panel TRSM,
+  //        panel pack + broadcasts, steps}
+  void read_chain_profile(double out[6]);
 
 private:
   void panel_step(int k, bool wait_column);
@@ -155,6 +159,9 @@ private:
   std::vector<double> prof_flops_;
   size_t prof_used_ = 0;
   double last_update_flops_ = 0.0;
+  std::vector<cudaEvent_t> chain_ev_;  // 6 stamps per step on stream H
+  size_t chain_used_ = 0;
+  void chain_stamp(int k, int which);
 };
 
 }  // namespace dlaf_b200

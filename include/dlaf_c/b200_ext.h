@@ -28,6 +28,10 @@ DLAF_EXTERN_C long dlaf_b200_last_launch_count(int ctx) DLAF_NOEXCEPT;
  * factorization (call after dlaf_b200_wait). */
 DLAF_EXTERN_C void dlaf_b200_set_profiling(int ctx, int enable) DLAF_NOEXCEPT;
 DLAF_EXTERN_C void dlaf_b200_read_profile(int ctx, double out[3]) DLAF_NOEXCEPT;
+/* Critical-path (stream H) breakdown of the last factorization, summed over the steps, in ms: out = {wait for the
+ * bulk + diagonal tile update, diagonal tile factorization, diagonal broadcast, wait for the column + panel TRSM,
+ * panel pack + broadcasts, number of steps}. */
+DLAF_EXTERN_C void dlaf_b200_read_chain_profile(int ctx, double out[6]) DLAF_NOEXCEPT;
 /* fp64 tensor-pipe (DMMA.8x8x4) issue-rate peak of the current device, TFLOP/s, measured now. */
 DLAF_EXTERN_C double dlaf_b200_measure_fp64_tensor_peak_tflops(void) DLAF_NOEXCEPT;
 

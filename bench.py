@@ -288,10 +288,20 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (bulk trailing update, DMMA GEMM)
     peak = pkg.measure_fp64_tensor_peak_tflops()
     achieved = (prof_fl / (prof_ms * 1e-3) / 1e12) if prof_ms > 0 else None
+    traffic, traffic_note = None, None
+    try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (one launch)
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_bulk_final.json")) as f:
+            cap = json.load(f)
+        traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
+        traffic_note = (f"ncu capture of ONE launch: {cap['launch']}; algorithmic bytes of that launch "
+                        f"{cap['algorithmic_bytes']} (C lower triangle read+write + panel), DMMA pipe active "
+                        f"{cap['dmma_pipe_active_pct']} %, L2 hit {cap['l2_hit_pct']} %")
+    except Exception:
+        pass
     roofline = {
-        "kernel": "gemm_nt_f64_kernel (bulk trailing update, stream L)", "bound": "tensor",
+        "kernel": "gemm_nt_f64_kernel<GemmCfg<64,64,16,3,4,2,2>> (bulk trailing update, stream L)", "bound": "tensor",
         "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-        "traffic": None,
+        "traffic": traffic, "traffic_note": traffic_note,
         "peak_source": "measured now on this GPU: DMMA.8x8x4 issue-rate microbenchmark (dlaf_b200_measure_fp64_tensor_peak_tflops); "
                        "MEASURED_PEAKS.json holds no fp64 figure (bf16 cuBLAS + HBM copy only); nominal B200 fp64 = 40 TFLOP/s",
         "launches_timed": prof_n, "critical_path_ms_last_step": chain, "kernel_ms_per_step": prof_ms / K if K else None,

@@ -63,10 +63,13 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
   *h_info_ = 0;
   if constexpr (std::is_same_v<T, float>) {
     // DLAF_B200_S_SIMT=1 keeps the SIMT fp32 kernel everywhere (A/B measurements)
-    use_tf32_ = geo_.P * geo_.Q == 1 && nt_ > 1 && std::getenv("DLAF_B200_S_SIMT") == nullptr;
+    use_tf32_ = nt_ > 1 && ltr_ > 0 && ltc_ > 0 && std::getenv("DLAF_B200_S_SIMT") == nullptr;
     if (use_tf32_)
-      for (int i = 0; i < 2; ++i)
+      for (int i = 0; i < 2; ++i) {
         split_[i].allocate(static_cast<long>(ltr_) * nbp_, nbp_);
+        if (geo_.P > 1)
+          splitT_[i].allocate(static_cast<long>(ltc_) * nbp_, nbp_);
+      }
   }
 }
 
@@ -103,8 +106,10 @@ PotrfEngine<T>::~PotrfEngine() {
   for (auto e : chain_ev_)
     cudaEventDestroy(e);
   if constexpr (std::is_same_v<T, float>) {
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 2; ++i) {
       split_[i].release();
+      splitT_[i].release();
+    }
   }
   cudaFree(own_slab_);
   cudaFree(d_info_);
@@ -347,7 +352,7 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
         DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evC_[(k - 1) % 2], 0));
       trsm_panel(tile_ptr(li1, lkc), ld_, mt * nbp_, tkk, ldt, w, sH_);
       if constexpr (std::is_same_v<T, float>) {
-        if (use_tf32_ && k < nt_ - 1) {
+        if (use_tf32_ && k < nt_ - 1 && P * Q == 1) {
           split_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sH_);
           ++launches_;
         }
@@ -383,6 +388,19 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
                                       col_comm_, sH_));
       }
       DLAF_NCCL_CHECK(ncclGroupEnd());
+    }
+  }
+  if constexpr (std::is_same_v<T, float>) {
+    if (use_tf32_ && k < nt_ - 1 && P * Q > 1) {
+      // split the (tile-contiguous) panel workspaces every rank now holds
+      if (mt > 0) {
+        split_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sH_, nbp_, static_cast<long>(tsz));
+        ++launches_;
+      }
+      if (P > 1 && ltc_ - lj1 > 0) {
+        splitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sH_, nbp_, static_cast<long>(tsz));
+        ++launches_;
+      }
     }
   }
   chain_stamp(k, 5);
@@ -460,9 +478,15 @@ void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows
   }
   if constexpr (std::is_same_v<T, float>) {
     if (use_tf32_) {
-      // 1 x 1 grid: panel row index = local tile row - li1, transposed panel row = tile column - li1
-      launch_gemm_tf32x3(a, split_[slot], static_cast<long>(ri0 - li1) * nbp_, split_[slot],
-                         static_cast<long>(cj0 - li1) * nbp_, st);
+      // A rows: panel row index = (local tile row - li1) * nbp. B rows: 1 x 1 grid and P == 1 alias the column
+      // panel (tile gj sits at index gj - (k+1), consecutive local columns Q tiles apart); P > 1 uses the
+      // transposed-panel split (tile index = local column - lj1).
+      const long a_row = static_cast<long>(ri0 - li1) * nbp_;
+      if (P > 1)
+        launch_gemm_tf32x3(a, split_[slot], a_row, splitT_[slot], static_cast<long>(cj0 - lj1) * nbp_, st);
+      else
+        launch_gemm_tf32x3(a, split_[slot], a_row, split_[slot], static_cast<long>(gj0 - (k + 1)) * nbp_, st,
+                           static_cast<long>(Q) * nbp_);
       ++launches_;
       return;
     }

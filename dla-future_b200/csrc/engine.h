@@ -150,7 +150,8 @@ private:
   // fp32 only: tcgen05 3xTF32 trailing update (gemm_tf32_tcgen05.cu) — the panel of step k is split into
   // K-major hi/lo parts right after its TRSM (two round-robin slots like the panel workspaces)
   bool use_tf32_ = false;
-  Tf32Split split_[2];
+  Tf32Split split_[2];   // column panel (rows = my local panel rows)
+  Tf32Split splitT_[2];  // transposed panel (P > 1 only: tiles (j,k) for my local columns j)
   int* d_info_ = nullptr;
   int* h_info_ = nullptr;
   long launches_ = 0;

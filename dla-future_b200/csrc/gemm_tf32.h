@@ -19,13 +19,17 @@ struct Tf32Split {
 
   void allocate(long rows_max, int kdim);
   void release();
-  // x: nrows x kdim, column-major (leading dimension ld) -> hi / lo rows [0, nrows)
-  void split(const float* x, long ld, long nrows, cudaStream_t s);
+  // x: nrows x kdim, column-major (leading dimension ld) -> hi / lo rows [0, nrows).
+  // tile_rows / tile_stride describe tile-contiguous panel workspaces: row r of x lives at
+  // x + (r / tile_rows) * tile_stride + r % tile_rows (tile_stride == 0: plain column-major).
+  void split(const float* x, long ld, long nrows, cudaStream_t s, int tile_rows = 0, long tile_stride = 0);
 };
 
 // C = beta C + alpha A B^T with A = rows [a_row, a_row + M) of `sa`, B = rows [b_row, b_row + N) of `sb`;
 // mask / geometry / C / alpha / beta taken from `a` (its A, B pointers are ignored).
+// b_tile_rows: distance in rows of `sb` between consecutive nbp-tiles of B (nbp when contiguous; Q * nbp when the
+// transposed panel aliases every Q-th tile of the column panel, the P == 1 case).
 void launch_gemm_tf32x3(const GemmArgsT<float>& a, const Tf32Split& sa, long a_row, const Tf32Split& sb, long b_row,
-                        cudaStream_t stream);
+                        cudaStream_t stream, long b_tile_rows = 0);
 
 }  // namespace dlaf_b200

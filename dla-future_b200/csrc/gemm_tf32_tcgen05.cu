@@ -107,6 +107,8 @@ struct Tf32Params {
   float alpha, beta;
   GemmArgsT<float> g;  // mask / geometry (A, B, C pointers of g are unused here)
   int a_row, b_row;    // row of A(0,:) / B(0,:) inside the split arrays
+  int nbp;             // tile edge
+  int b_tile_rows;     // rows of the B split array between consecutive tiles (== nbp when contiguous)
 };
 
 __global__ void __launch_bounds__(TTHREADS, 1)
@@ -161,8 +163,9 @@ __global__ void __launch_bounds__(TTHREADS, 1)
         uint8_t* st = tiles + s * STAGE_BYTES;
         tma_load_2d(st, &mAh, &full[s], kb * TBK, p.a_row + row0);
         tma_load_2d(st + TILE_BYTES, &mAl, &full[s], kb * TBK, p.a_row + row0);
-        tma_load_2d(st + 2 * TILE_BYTES, &mBh, &full[s], kb * TBK, p.b_row + col0);
-        tma_load_2d(st + 3 * TILE_BYTES, &mBl, &full[s], kb * TBK, p.b_row + col0);
+        const int brow = p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp;
+        tma_load_2d(st + 2 * TILE_BYTES, &mBh, &full[s], kb * TBK, brow);
+        tma_load_2d(st + 3 * TILE_BYTES, &mBl, &full[s], kb * TBK, brow);
       }
     }
   }
@@ -255,14 +258,15 @@ __global__ void __launch_bounds__(TTHREADS, 1)
 
 // x (rows x k, column-major with leading dimension ld) -> hi, lo (rows x k, ROW-major: k contiguous)
 __global__ void split_tf32_kernel(const float* __restrict__ x, long ld, int rows, int kdim, float* __restrict__ hi,
-                                  float* __restrict__ lo) {
+                                  float* __restrict__ lo, int tile_rows, long tile_stride) {
   __shared__ float t[32][33];
   const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     const int r = r0 + tx, k = k0 + ty + i;
-    t[ty + i][tx] = (r < rows && k < kdim) ? x[r + static_cast<long>(k) * ld] : 0.f;
+    const long roff = tile_stride ? (r / tile_rows) * tile_stride + r % tile_rows : r;
+    t[ty + i][tx] = (r < rows && k < kdim) ? x[roff + static_cast<long>(k) * ld] : 0.f;
   }
   __syncthreads();
 #pragma unroll
@@ -321,19 +325,20 @@ void Tf32Split::release() {
   hi = lo = nullptr;
 }
 
-void Tf32Split::split(const float* x, long ld, long nrows, cudaStream_t s) {
+void Tf32Split::split(const float* x, long ld, long nrows, cudaStream_t s, int tile_rows, long tile_stride) {
   DLAF_B200_ASSERT(nrows <= rows, "split buffer too small");
   if (nrows <= 0)
     return;
   dim3 grid(static_cast<unsigned>((nrows + 31) / 32), static_cast<unsigned>((kdim + 31) / 32)), block(32, 8);
-  split_tf32_kernel<<<grid, block, 0, s>>>(x, ld, static_cast<int>(nrows), kdim, hi, lo);
+  split_tf32_kernel<<<grid, block, 0, s>>>(x, ld, static_cast<int>(nrows), kdim, hi, lo, tile_rows > 0 ? tile_rows : 1,
+                                           tile_stride);
   DLAF_CUDA_CHECK(cudaGetLastError());
 }
 
 static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
 
 void launch_gemm_tf32x3(const GemmArgsT<float>& a, const Tf32Split& sa, long a_row, const Tf32Split& sb, long b_row,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, long b_tile_rows) {
   if (a.M <= 0 || a.N <= 0)
     return;
   DLAF_B200_ASSERT(a.M % TBM == 0 && a.N % TBN == 0 && a.K % TBK == 0 && a.K == sa.kdim && a.K == sb.kdim,
@@ -352,6 +357,8 @@ void launch_gemm_tf32x3(const GemmArgsT<float>& a, const Tf32Split& sa, long a_r
   p.g = a;
   p.a_row = static_cast<int>(a_row);
   p.b_row = static_cast<int>(b_row);
+  p.nbp = a.nbp;
+  p.b_tile_rows = static_cast<int>(b_tile_rows > 0 ? b_tile_rows : a.nbp);
   dim3 grid(a.M / TBM, a.N / TBN);
   gemm_tf32x3_kernel<<<grid, TTHREADS, TSMEM_BYTES, stream>>>(
       *reinterpret_cast<const CUtensorMap*>(sa.map_hi), *reinterpret_cast<const CUtensorMap*>(sa.map_lo),

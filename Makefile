@@ -12,7 +12,7 @@ CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
 OBJS     := $(CU_OBJS) $(CPP_OBJS)
 HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h)
 
-all: $(LIB) tools/gpu_kernel_test miniapp/miniapp_cholesky
+all: $(LIB) tools/gpu_kernel_test tools/gpu_chain_test tools/cusolver_potrf_ref miniapp/miniapp_cholesky
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -31,11 +31,18 @@ $(LIB): $(OBJS)
 tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_tile.o build/gemm_tf32_tcgen05.o $(HDRS)
 	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/potrf_tile.o build/gemm_tf32_tcgen05.o -lcublas -o $@
 
+tools/gpu_chain_test: tools/gpu_chain_test.cu build/gemm_dmma.o $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o -o $@
+
+# vendor-library GPU reference (measurement aid only; nothing in the product links cuSOLVER)
+tools/cusolver_potrf_ref: tools/cusolver_potrf_ref.cu
+	$(NVCC) $(NVCCFLAGS) $< -lcusolver -lcublas -o $@
+
 # The driver is plain C++ against include/dlaf (header-only surface) + the C-ABI library.
 miniapp/miniapp_cholesky: miniapp/miniapp_cholesky.cpp $(LIB) $(wildcard include/dlaf/*.h) $(wildcard include/dlaf/*/*.h)
 	g++ $(CXXFLAGS) $< -o $@ -L$(LIBDIR) -ldlaf_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread
 
 clean:
-	rm -rf build tools/gpu_kernel_test $(LIBDIR)/*.so
+	rm -rf build tools/gpu_kernel_test tools/gpu_chain_test tools/cusolver_potrf_ref $(LIBDIR)/*.so
 
 .PHONY: all clean

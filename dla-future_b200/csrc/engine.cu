@@ -3,6 +3,7 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <string>
 #include <type_traits>
 
 #include "comm.h"
@@ -104,6 +105,8 @@ PotrfEngine<T>::~PotrfEngine() {
   for (auto e : prof_ev_)
     cudaEventDestroy(e);
   for (auto e : chain_ev_)
+    cudaEventDestroy(e);
+  for (auto e : diag_ev_)
     cudaEventDestroy(e);
   if constexpr (std::is_same_v<T, float>) {
     for (int i = 0; i < 2; ++i) {
@@ -210,13 +213,27 @@ void PotrfEngine<T>::gemm(const GemmArgsT<T>& a, cudaStream_t st) {
 
 // Diagonal tile (nbp x nbp) = ns diagonal blocks of G: block Cholesky + inverse (potrf_tile.cu), the
 // blocks below via GEMM with the inverse, the rest of the tile via a masked SYRK-shaped GEMM.
+// (Measured and dropped: a one-block look-ahead inside the tile on a second stream — the critical stream keeps
+// two dependent launches per block either way, 349 vs 342 us per tile in isolation, profiles/r01_chain_*.)
 template <class T>
 void PotrfEngine<T>::factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_t st) {
   for (int j = 0; j < ns_; ++j) {
     T* tjj = tile + static_cast<long>(j) * G * (1 + ld);
     T* wj = w + static_cast<long>(j) * G * G;
+    if (profiling_) {  // per-launch in-situ time of the diagonal-block kernel (DLAF_B200_CHAIN_DEBUG prints the sum)
+      while (diag_ev_.size() < diag_used_ + 2) {
+        cudaEvent_t e;
+        DLAF_CUDA_CHECK(cudaEventCreate(&e));
+        diag_ev_.push_back(e);
+      }
+      DLAF_CUDA_CHECK(cudaEventRecord(diag_ev_[diag_used_], st));
+    }
     launch_potrf_inv<T>(tjj, ld, wj, G, d_info_, k * geo_.nb + j * G, st);
     ++launches_;
+    if (profiling_) {
+      DLAF_CUDA_CHECK(cudaEventRecord(diag_ev_[diag_used_ + 1], st));
+      diag_used_ += 2;
+    }
     const int m = (ns_ - 1 - j) * G;
     if (m == 0)
       break;
@@ -260,6 +277,31 @@ void PotrfEngine<T>::factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_
 // block substitution over the ns diagonal blocks: every step is a tensor-core GEMM.
 template <class T>
 void PotrfEngine<T>::trsm_panel(T* b, long ldb, int m, const T* tkk, long ldt, const T* w, cudaStream_t st) {
+  if constexpr (std::is_same_v<T, double> || std::is_same_v<T, double2>) {
+    // one launch: every CTA runs the whole block substitution for its own rows (gemm_dmma.cuh, gemm_zdmma.cu);
+    // DLAF_B200_TRSM=steps keeps the 2*ns-1 separate GEMM launches (A/B measurements)
+    static const bool fused = [] {
+      const char* e = std::getenv("DLAF_B200_TRSM");
+      return e == nullptr || std::string(e) != "steps";
+    }();
+    if (fused && m > 0) {
+      if constexpr (std::is_same_v<T, double>) {
+        TrsmFusedArgs a{};
+        a.B = b;
+        a.ldb = ldb;
+        a.T = tkk;
+        a.ldt = ldt;
+        a.W = w;
+        a.ns = ns_;
+        launch_trsm_fused_f64(a, m, st);
+      }
+      else {
+        launch_trsm_fused_z(b, ldb, m, tkk, ldt, w, ns_, st);
+      }
+      ++launches_;
+      return;
+    }
+  }
   for (int j = 0; j < ns_; ++j) {
     T* bj = b + static_cast<long>(j) * G * ldb;
     if (j > 0) {
@@ -665,6 +707,16 @@ void PotrfEngine<T>::read_chain_profile(double out[6]) {
     }
     out[5] += 1.0;
   }
+  if (std::getenv("DLAF_B200_CHAIN_DEBUG")) {
+    double pot = 0;
+    for (size_t i = 0; i + 1 < diag_used_; i += 2) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, diag_ev_[i], diag_ev_[i + 1]) == cudaSuccess)
+        pot += ms;
+    }
+    std::fprintf(stderr, "[dlaf_b200] chain debug: %zu diagonal-block kernels, in-situ sum %.3f ms (avg %.1f us); diag tiles %.3f ms\n",
+                 diag_used_ / 2, pot, diag_used_ ? pot * 2000.0 / diag_used_ : 0.0, out[1]);
+  }
 }
 
 template <class T>
@@ -686,6 +738,7 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   launches_ = 0;
   prof_used_ = 0;
   chain_used_ = 0;
+  diag_used_ = 0;
   if (nt_ == 0)
     return;
   if (!external_)

@@ -162,6 +162,8 @@ private:
   double last_update_flops_ = 0.0;
   std::vector<cudaEvent_t> chain_ev_;  // 6 stamps per step on stream H
   size_t chain_used_ = 0;
+  std::vector<cudaEvent_t> diag_ev_;  // (begin, end) per diagonal-block kernel (profiling mode)
+  size_t diag_used_ = 0;
   void chain_stamp(int k, int which);
 };
 

@@ -58,6 +58,22 @@ __host__ __device__ inline int classify_tile(const GemmArgsT<T>& p, int row0, in
 #include <cuda_runtime.h>
 
 namespace dlaf_b200 {
+// Fused panel TRSM (fp64, gemm_dmma.cuh: trsm_fused_f64_kernel): B (m x ns*128 row panel) <- B * L^-T in ONE launch.
+struct TrsmFusedArgs {
+  double* B;        // m x ns*G row panel, column-major
+  long ldb;
+  const double* T;  // factored diagonal tile (lower), column-major
+  long ldt;
+  const double* W;  // ns inverted diagonal blocks, each G x G contiguous (ld = G)
+  int ns;
+};
+// m % 32 == 0, 16-byte aligned operands with even leading dimensions.
+void launch_trsm_fused_f64(const TrsmFusedArgs& args, int m, cudaStream_t stream);
+
+// complex<double> flavour (gemm_zdmma.cu: trsm_fused_z_kernel), 64 x 64 diagonal blocks, m % 64 == 0.
+void launch_trsm_fused_z(double2* b, long ldb, int m, const double2* t, long ldt, const double2* w, int ns,
+                         cudaStream_t stream);
+
 // Kernel entry point per element type (explicit specialisations live next to the kernels).
 template <class T>
 void launch_gemm_nt(const GemmArgsT<T>& args, cudaStream_t stream);

@@ -67,6 +67,24 @@ void launch_gemm_nt_f64(const GemmArgs& a, cudaStream_t stream) {
     launch_gemm_nt_f64_cfg(a, bulk_cfg, stream);
 }
 
+void launch_trsm_fused_f64(const TrsmFusedArgs& a, int m, cudaStream_t stream) {
+  using Cfg = GemmCfg32x128w4;
+  if (m <= 0 || a.ns <= 0)
+    return;
+  DLAF_B200_ASSERT(m % Cfg::BM == 0, "fused TRSM: rows must be a multiple of the CTA row block");
+  DLAF_B200_ASSERT(a.ldb % 2 == 0 && a.ldt % 2 == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.T) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+                   "fused TRSM: 16-byte aligned operands");
+  static bool configured = false;
+  if (!configured) {
+    DLAF_CUDA_CHECK(cudaFuncSetAttribute(trsm_fused_f64_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  trsm_fused_f64_kernel<Cfg><<<m / Cfg::BM, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+
 template <>
 void launch_gemm_nt<double>(const GemmArgsT<double>& a, cudaStream_t stream) {
   launch_gemm_nt_f64(a, stream);

@@ -63,44 +63,47 @@ struct GemmCfg {
   static constexpr int FM = WM / 8, FN = WN / 8;              // 8x8 fragments per warp
 };
 
+// One CTA tile of the NT product, already resolved to this CTA's operands (the body shared by the plain GEMM
+// kernel and the fused panel-TRSM kernel below).
+struct GemmTileOp {
+  const double* Ag;  // first row of this CTA's A rows (k = 0)
+  long lda;
+  const double* Bg;  // first row of this CTA's B rows (k = 0)
+  long ldb;
+  double* Cg;        // C(row0, col0)
+  long ldc;
+  int KT;            // K / BK
+  double alpha, beta;
+  int cls;           // 1 = full tile, 2 = straddles the diagonal (element mask on grow0 / gcol0)
+  long grow0, gcol0;
+};
+
 template <class Cfg>
-__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(const GemmArgs p) {
+__device__ __forceinline__ void gemm_nt_f64_tile(const GemmTileOp& t, double* smem) {
   using namespace gemm_detail;
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int FM = Cfg::FM, FN = Cfg::FN;
 
-  extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + STAGES * Cfg::A_STAGE;
 
-  const int row0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
-  long grow0, gcol0;
-  const int cls = classify_tile(p, row0, col0, BM, BN, grow0, gcol0);
-  if (cls == 0)
-    return;
-
-  if (p.dbg_stagger_ns > 0) {
-    const unsigned lin = blockIdx.x + blockIdx.y * gridDim.x;
-    if (lin >= 148 && lin < 296)
-      __nanosleep(p.dbg_stagger_ns);
-  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
   const int wm0 = (warp % Cfg::WARPS_M) * Cfg::WM;
   const int wn0 = (warp / Cfg::WARPS_M) * Cfg::WN;
 
-  const double* Ag = p.A + (p.a_ts ? (row0 / p.nbp) * p.a_ts + row0 % p.nbp : row0);
-  const double* Bg = p.B + (p.b_ts ? (col0 / p.nbp) * p.b_ts + col0 % p.nbp : col0);
-  const int KT = p.K / BK;
+  const double* Ag = t.Ag;
+  const double* Bg = t.Bg;
+  const long lda = t.lda, ldb = t.ldb, ldc = t.ldc;
+  const int KT = t.KT;
 
-  if (p.beta != 0.0) {
+  if (t.beta != 0.0) {
     // Pull the C tile towards L2 now; the epilogue reads it ~K/16 stages later.
-    const double* Cg0 = p.C + row0 + static_cast<long>(col0) * p.ldc;
 #pragma unroll
     for (int i = 0; i < (BM / 16) * BN / Cfg::THREADS; ++i) {
       const int l = tid + i * Cfg::THREADS;
       const int col = l / (BM / 16), seg = l % (BM / 16);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(Cg0 + seg * 16 + static_cast<long>(col) * p.ldc));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(t.Cg + seg * 16 + static_cast<long>(col) * ldc));
     }
   }
 
@@ -112,13 +115,13 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(co
     for (int i = 0; i < (BK * BM / 2) / Cfg::THREADS; ++i) {
       const int c = tid + i * Cfg::THREADS;
       const int k = c / (BM / 2), m2 = c % (BM / 2);
-      cp_async16(as + k * Cfg::LDA_S + 2 * m2, Ag + static_cast<long>(k0 + k) * p.lda + 2 * m2);
+      cp_async16(as + k * Cfg::LDA_S + 2 * m2, Ag + static_cast<long>(k0 + k) * lda + 2 * m2);
     }
 #pragma unroll
     for (int i = 0; i < (BK * BN / 2) / Cfg::THREADS; ++i) {
       const int c = tid + i * Cfg::THREADS;
       const int k = c / (BN / 2), n2 = c % (BN / 2);
-      cp_async16(bs + k * Cfg::LDB_S + 2 * n2, Bg + static_cast<long>(k0 + k) * p.ldb + 2 * n2);
+      cp_async16(bs + k * Cfg::LDB_S + 2 * n2, Bg + static_cast<long>(k0 + k) * ldb + 2 * n2);
     }
   };
 
@@ -183,10 +186,11 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(co
         Cs[(wn0 + 8 * j + 2 * tig + e) * LDC_S + wm0 + 8 * i + g] = acc[i][j][e];
   __syncthreads();
 
-  const bool use_beta = (p.beta != 0.0);
+  const bool use_beta = (t.beta != 0.0);
+  const double alpha = t.alpha, beta = t.beta;
   constexpr int CHUNKS = BM * BN / 2 / Cfg::THREADS;  // 16-byte chunks per thread
   constexpr int BATCH = 8;
-  double* Cg = p.C + row0 + static_cast<long>(col0) * p.ldc;
+  double* Cg = t.Cg;
 #pragma unroll 1
   for (int b0 = 0; b0 < CHUNKS; b0 += BATCH) {
     double2 cv[BATCH];
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(co
       for (int b = 0; b < BATCH; ++b) {
         const int q = tid + (b0 + b) * Cfg::THREADS;
         const int col = q / (BM / 2), m2 = q % (BM / 2);
-        cv[b] = *reinterpret_cast<const double2*>(Cg + 2 * m2 + static_cast<long>(col) * p.ldc);
+        cv[b] = *reinterpret_cast<const double2*>(Cg + 2 * m2 + static_cast<long>(col) * ldc);
       }
     }
 #pragma unroll
@@ -204,24 +208,98 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(co
       const int col = q / (BM / 2), m2 = q % (BM / 2);
       const double2 a = *reinterpret_cast<const double2*>(Cs + col * LDC_S + 2 * m2);
       double2 v;
-      v.x = p.alpha * a.x;
-      v.y = p.alpha * a.y;
+      v.x = alpha * a.x;
+      v.y = alpha * a.y;
       if (use_beta) {
-        v.x += p.beta * cv[b].x;
-        v.y += p.beta * cv[b].y;
+        v.x += beta * cv[b].x;
+        v.y += beta * cv[b].y;
       }
-      double* dst = Cg + 2 * m2 + static_cast<long>(col) * p.ldc;
-      if (cls == 1) {
+      double* dst = Cg + 2 * m2 + static_cast<long>(col) * ldc;
+      if (t.cls == 1) {
         *reinterpret_cast<double2*>(dst) = v;
       }
       else {  // tile straddles the diagonal: element mask, never touch the other triangle
-        const long gr = grow0 + 2 * m2, gc = gcol0 + col;
+        const long gr = t.grow0 + 2 * m2, gc = t.gcol0 + col;
         if (gr >= gc)
           dst[0] = v.x;
         if (gr + 1 >= gc)
           dst[1] = v.y;
       }
     }
+  }
+}
+
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(const GemmArgs p) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK;
+  extern __shared__ __align__(16) double smem[];
+
+  const int row0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  GemmTileOp t;
+  t.cls = classify_tile(p, row0, col0, BM, BN, t.grow0, t.gcol0);
+  if (t.cls == 0)
+    return;
+
+  if (p.dbg_stagger_ns > 0) {
+    const unsigned lin = blockIdx.x + blockIdx.y * gridDim.x;
+    if (lin >= 148 && lin < 296)
+      __nanosleep(p.dbg_stagger_ns);
+  }
+  t.Ag = p.A + (p.a_ts ? (row0 / p.nbp) * p.a_ts + row0 % p.nbp : row0);
+  t.lda = p.lda;
+  t.Bg = p.B + (p.b_ts ? (col0 / p.nbp) * p.b_ts + col0 % p.nbp : col0);
+  t.ldb = p.ldb;
+  t.Cg = p.C + row0 + static_cast<long>(col0) * p.ldc;
+  t.ldc = p.ldc;
+  t.KT = p.K / BK;
+  t.alpha = p.alpha;
+  t.beta = p.beta;
+  gemm_nt_f64_tile<Cfg>(t, smem);
+}
+
+// Panel TRSM in ONE launch:  B <- B * L^-T  for a row panel B (m x ns*G) against the factored diagonal tile
+// L (ns*G x ns*G, lower) whose G x G diagonal blocks come pre-inverted (W, from potrf_inv). Rows are
+// independent in a right-side triangular solve, so each CTA owns BM rows of B and runs the whole block
+// substitution for them, phase after phase, with the tile body above:
+//     for j = 0 .. ns-1:   B_j -= sum_{i<j} X_i L_ji^T   (K = j*G;  X_i are this CTA's own finished rows)
+//                          X_j  = B_j inv(L_jj)^T         (K = G, in place)
+// It replaces 2*ns-1 dependent launches per panel on the critical path (reference: one cublas?trsm per
+// tile, include/dlaf/factorization/cholesky/impl.h:55-67, blas/tile.h:337-349). Same shared-memory and
+// register footprint as one in-place product, so it slots in next to the bulk update's CTAs.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) trsm_fused_f64_kernel(const TrsmFusedArgs p) {
+  constexpr int G = Cfg::BN;  // one CTA column == one diagonal block
+  extern __shared__ __align__(16) double smem[];
+  double* rows = p.B + static_cast<long>(blockIdx.x) * Cfg::BM;
+  GemmTileOp t;
+  t.cls = 1;
+  t.grow0 = t.gcol0 = 0;
+  t.lda = p.ldb;
+  t.ldc = p.ldb;
+  for (int j = 0; j < p.ns; ++j) {
+    double* bj = rows + static_cast<long>(j) * G * p.ldb;
+    if (j > 0) {
+      t.Ag = rows;
+      t.Bg = p.T + static_cast<long>(j) * G;  // row block j of L, columns [0, j*G)
+      t.ldb = p.ldt;
+      t.Cg = bj;
+      t.KT = j * G / Cfg::BK;
+      t.alpha = -1.0;
+      t.beta = 1.0;
+      gemm_nt_f64_tile<Cfg>(t, smem);
+      __threadfence_block();
+      __syncthreads();  // B_j (global) and the staging ring are handed to the next phase
+    }
+    t.Ag = bj;
+    t.Bg = p.W + static_cast<long>(j) * G * G;
+    t.ldb = G;
+    t.Cg = bj;
+    t.KT = G / Cfg::BK;
+    t.alpha = 1.0;
+    t.beta = 0.0;
+    gemm_nt_f64_tile<Cfg>(t, smem);
+    __threadfence_block();
+    __syncthreads();  // X_j is read as an A operand by the following phases
   }
 }
 

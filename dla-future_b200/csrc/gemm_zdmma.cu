@@ -42,23 +42,32 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(ZTHREADS, 2) gemm_nt_z_kernel(const GemmArgsT<double2> p) {
-  extern __shared__ __align__(16) double2 zsmem[];
+// One CTA tile, already resolved to this CTA's operands (shared by the plain kernel and the fused panel TRSM).
+struct ZTileOp {
+  const double2* Ag;
+  long lda;
+  const double2* Bg;
+  long ldb;
+  double2* Cg;
+  long ldc;
+  int KT;
+  double alpha, beta;
+  int cls;         // 1 = full tile, 2 = straddles the diagonal
+  int herm_diag;   // force a real diagonal (zherk)
+  long grow0, gcol0;
+};
+
+__device__ __forceinline__ void gemm_nt_z_tile(const ZTileOp& t, double2* zsmem) {
   double2* As = zsmem;
   double2* Bs = zsmem + ZSTAGES * ZSTAGE;
-
-  const int row0 = blockIdx.x * ZBM, col0 = blockIdx.y * ZBN;
-  long grow0, gcol0;
-  const int cls = classify_tile(p, row0, col0, ZBM, ZBN, grow0, gcol0);
-  if (cls == 0)
-    return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
   const int wm0 = (warp & 1) * 32, wn0 = (warp >> 1) * 32;
 
-  const double2* Ag = p.A + (p.a_ts ? (row0 / p.nbp) * p.a_ts + row0 % p.nbp : row0);
-  const double2* Bg = p.B + (p.b_ts ? (col0 / p.nbp) * p.b_ts + col0 % p.nbp : col0);
-  const int KT = p.K / ZBK;
+  const double2* Ag = t.Ag;
+  const double2* Bg = t.Bg;
+  const long lda = t.lda, ldb = t.ldb, ldc = t.ldc;
+  const int KT = t.KT;
 
   auto load_stage = [&](int slot, int kt) {
     const int k0 = kt * ZBK;
@@ -68,13 +77,13 @@ __global__ void __launch_bounds__(ZTHREADS, 2) gemm_nt_z_kernel(const GemmArgsT<
     for (int i = 0; i < ZBK * ZBM / ZTHREADS; ++i) {
       const int c = tid + i * ZTHREADS;
       const int k = c / ZBM, m = c % ZBM;
-      cp_async16(as + k * ZLD + m, Ag + static_cast<long>(k0 + k) * p.lda + m);
+      cp_async16(as + k * ZLD + m, Ag + static_cast<long>(k0 + k) * lda + m);
     }
 #pragma unroll
     for (int i = 0; i < ZBK * ZBN / ZTHREADS; ++i) {
       const int c = tid + i * ZTHREADS;
       const int k = c / ZBN, n = c % ZBN;
-      cp_async16(bs + k * ZLD + n, Bg + static_cast<long>(k0 + k) * p.ldb + n);
+      cp_async16(bs + k * ZLD + n, Bg + static_cast<long>(k0 + k) * ldb + n);
     }
   };
 
@@ -139,8 +148,11 @@ __global__ void __launch_bounds__(ZTHREADS, 2) gemm_nt_z_kernel(const GemmArgsT<
         Cs[(wn0 + 8 * j + 2 * tig + e) * ZLDC + wm0 + 8 * i + g] = make_double2(cr[i][j][e], ci[i][j][e]);
   __syncthreads();
 
-  const bool use_beta = (p.beta != 0.0);
-  double2* Cg = p.C + row0 + static_cast<long>(col0) * p.ldc;
+  const bool use_beta = (t.beta != 0.0);
+  const double alpha = t.alpha, beta = t.beta;
+  const int cls = t.cls;
+  const long grow0 = t.grow0, gcol0 = t.gcol0;
+  double2* Cg = t.Cg;
   constexpr int CHUNKS = ZBM * ZBN / ZTHREADS;  // complex elements per thread
   constexpr int BATCH = 8;
 #pragma unroll 1
@@ -150,7 +162,7 @@ __global__ void __launch_bounds__(ZTHREADS, 2) gemm_nt_z_kernel(const GemmArgsT<
 #pragma unroll
       for (int b = 0; b < BATCH; ++b) {
         const int q = tid + (b0 + b) * ZTHREADS;
-        cv[b] = Cg[(q % ZBM) + static_cast<long>(q / ZBM) * p.ldc];
+        cv[b] = Cg[(q % ZBM) + static_cast<long>(q / ZBM) * ldc];
       }
     }
 #pragma unroll
@@ -160,15 +172,84 @@ __global__ void __launch_bounds__(ZTHREADS, 2) gemm_nt_z_kernel(const GemmArgsT<
       if (cls == 2 && (grow0 + r) < (gcol0 + c))
         continue;
       const double2 a = Cs[c * ZLDC + r];
-      double2 v = make_double2(p.alpha * a.x, p.alpha * a.y);
+      double2 v = make_double2(alpha * a.x, alpha * a.y);
       if (use_beta) {
-        v.x += p.beta * cv[b].x;
-        v.y += p.beta * cv[b].y;
+        v.x += beta * cv[b].x;
+        v.y += beta * cv[b].y;
       }
-      if (cls == 2 && p.mask == kMaskLower && (grow0 + r) == (gcol0 + c))
+      if (cls == 2 && t.herm_diag && (grow0 + r) == (gcol0 + c))
         v.y = 0.0;  // the diagonal of a Hermitian update is real (zherk)
-      Cg[r + static_cast<long>(c) * p.ldc] = v;
+      Cg[r + static_cast<long>(c) * ldc] = v;
     }
+  }
+}
+
+__global__ void __launch_bounds__(ZTHREADS, 2) gemm_nt_z_kernel(const GemmArgsT<double2> p) {
+  extern __shared__ __align__(16) double2 zsmem[];
+  const int row0 = blockIdx.x * ZBM, col0 = blockIdx.y * ZBN;
+  ZTileOp t;
+  t.cls = classify_tile(p, row0, col0, ZBM, ZBN, t.grow0, t.gcol0);
+  if (t.cls == 0)
+    return;
+  t.herm_diag = (p.mask == kMaskLower);
+  t.Ag = p.A + (p.a_ts ? (row0 / p.nbp) * p.a_ts + row0 % p.nbp : row0);
+  t.lda = p.lda;
+  t.Bg = p.B + (p.b_ts ? (col0 / p.nbp) * p.b_ts + col0 % p.nbp : col0);
+  t.ldb = p.ldb;
+  t.Cg = p.C + row0 + static_cast<long>(col0) * p.ldc;
+  t.ldc = p.ldc;
+  t.KT = p.K / ZBK;
+  t.alpha = p.alpha;
+  t.beta = p.beta;
+  gemm_nt_z_tile(t, zsmem);
+}
+
+// Panel TRSM in one launch (complex<double>), see trsm_fused_f64_kernel in gemm_dmma.cuh: each CTA owns ZBM rows
+// of the row panel B (m x ns*64) and runs the whole block substitution against the factored diagonal tile T
+// (lower) and its ns pre-inverted 64 x 64 diagonal blocks W:   X_j = (B_j - sum_{i<j} X_i L_ji^H) inv(L_jj)^H.
+struct ZTrsmFusedArgs {
+  double2* B;
+  long ldb;
+  const double2* T;
+  long ldt;
+  const double2* W;
+  int ns;
+};
+
+__global__ void __launch_bounds__(ZTHREADS, 2) trsm_fused_z_kernel(const ZTrsmFusedArgs p) {
+  constexpr int G = ZBN;
+  extern __shared__ __align__(16) double2 zsmem[];
+  double2* rows = p.B + static_cast<long>(blockIdx.x) * ZBM;
+  ZTileOp t;
+  t.cls = 1;
+  t.herm_diag = 0;
+  t.grow0 = t.gcol0 = 0;
+  t.lda = p.ldb;
+  t.ldc = p.ldb;
+  for (int j = 0; j < p.ns; ++j) {
+    double2* bj = rows + static_cast<long>(j) * G * p.ldb;
+    if (j > 0) {
+      t.Ag = rows;
+      t.Bg = p.T + static_cast<long>(j) * G;  // row block j of L, columns [0, j*G)
+      t.ldb = p.ldt;
+      t.Cg = bj;
+      t.KT = j * G / ZBK;
+      t.alpha = -1.0;
+      t.beta = 1.0;
+      gemm_nt_z_tile(t, zsmem);
+      __threadfence_block();
+      __syncthreads();
+    }
+    t.Ag = bj;
+    t.Bg = p.W + static_cast<long>(j) * G * G;
+    t.ldb = G;
+    t.Cg = bj;
+    t.KT = G / ZBK;
+    t.alpha = 1.0;
+    t.beta = 0.0;
+    gemm_nt_z_tile(t, zsmem);
+    __threadfence_block();
+    __syncthreads();
   }
 }
 
@@ -190,4 +271,21 @@ void launch_gemm_nt_z_dmma(const GemmArgsT<double2>& a, cudaStream_t stream) {
   DLAF_CUDA_CHECK(cudaGetLastError());
 }
 
+}  // namespace dlaf_b200
+
+namespace dlaf_b200 {
+void launch_trsm_fused_z(double2* b, long ldb, int m, const double2* t, long ldt, const double2* w, int ns,
+                         cudaStream_t stream) {
+  if (m <= 0 || ns <= 0)
+    return;
+  DLAF_B200_ASSERT(m % ZBM == 0, "fused TRSM: rows must be a multiple of the CTA row block");
+  static bool configured = false;
+  if (!configured) {
+    DLAF_CUDA_CHECK(cudaFuncSetAttribute(trsm_fused_z_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSMEM_BYTES));
+    configured = true;
+  }
+  const ZTrsmFusedArgs a{b, ldb, t, ldt, w, ns};
+  trsm_fused_z_kernel<<<m / ZBM, ZTHREADS, ZSMEM_BYTES, stream>>>(a);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
 }  // namespace dlaf_b200

@@ -7,12 +7,12 @@ CSRC      := dla-future_b200/csrc
 LIBDIR    := dla-future_b200/lib
 LIB       := $(LIBDIR)/libdlaf_b200.so
 
-CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/gemm_zdmma.o build/gemm_tf32_tcgen05.o build/potrf_tile.o build/layout.o build/engine.o build/peak.o build/check.o
+CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/gemm_zdmma.o build/gemm_tf32_tcgen05.o build/gemm_ozaki_i8.o build/potrf_tile.o build/layout.o build/engine.o build/peak.o build/check.o
 CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
 OBJS     := $(CU_OBJS) $(CPP_OBJS)
 HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h)
 
-all: $(LIB) tools/gpu_kernel_test tools/gpu_chain_test tools/cusolver_potrf_ref miniapp/miniapp_cholesky
+all: $(LIB) tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref miniapp/miniapp_cholesky
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -34,6 +34,9 @@ tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_ti
 tools/gpu_chain_test: tools/gpu_chain_test.cu build/gemm_dmma.o $(HDRS)
 	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o -o $@
 
+tools/gpu_ozaki_test: tools/gpu_ozaki_test.cu build/gemm_dmma.o build/gemm_ozaki_i8.o $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/gemm_ozaki_i8.o -o $@
+
 # vendor-library GPU reference (measurement aid only; nothing in the product links cuSOLVER)
 tools/cusolver_potrf_ref: tools/cusolver_potrf_ref.cu
 	$(NVCC) $(NVCCFLAGS) $< -lcusolver -lcublas -o $@
@@ -43,6 +46,6 @@ miniapp/miniapp_cholesky: miniapp/miniapp_cholesky.cpp $(LIB) $(wildcard include
 	g++ $(CXXFLAGS) $< -o $@ -L$(LIBDIR) -ldlaf_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread
 
 clean:
-	rm -rf build tools/gpu_kernel_test tools/gpu_chain_test tools/cusolver_potrf_ref $(LIBDIR)/*.so
+	rm -rf build tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref $(LIBDIR)/*.so
 
 .PHONY: all clean

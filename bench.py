@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=-1, help="end-to-end (host buffer) steps, default min(steps, 2)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-check", action="store_true")
+    p.add_argument("--no-gpu-reference", action="store_true", help="skip the cuSOLVER Dpotrf timing (tools/cusolver_potrf_ref)")
     p.add_argument("--cpu-sample-n", type=int, default=0, help="force the CPU sample size")
     return p.parse_args()
 
@@ -351,6 +352,24 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             cpu = {"value": None, "unit": "GFLOP/s", "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
 
+    # ---- vendor-library GPU reference on the same box, same run: monolithic cusolverDnDpotrf, the
+    # routine the reference's GPU backend calls per tile. Measurement aid (tools/cusolver_potrf_ref), never on the
+    # product path; absent binary -> null.
+    gpu_ref = None
+    exe = os.path.join(ROOT, "tools", "cusolver_potrf_ref")
+    if rank == 0 and world == 1 and not args.no_gpu_reference and os.path.exists(exe):
+        try:
+            del d_ref
+            torch.cuda.empty_cache()
+            r = subprocess.run([exe, str(n)], capture_output=True, text=True, timeout=300)
+            for ln in r.stdout.splitlines():
+                if " best:" in ln:
+                    tok = ln.split()
+                    gpu_ref = {"kind": "cusolverDnDpotrf (monolithic, device-resident, lower)", "ms": float(tok[3]),
+                               "value": float(tok[5]), "unit": "GFLOP/s", "n": n}
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] cusolver reference skipped: {e}")
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -362,6 +381,7 @@ def run_ours(args):
                        "timing": "CUDA events on the launching stream per step, summed over K steps, max over ranks",
                        "wall_s_incl_restore": wall},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_library_reference": gpu_ref,
             "residual_max_diff_over_max_a": residual,
             "residual_gate_eps_n": float(np.finfo(np.float64).eps * n),
             "step_ms": step_ms,

@@ -12,6 +12,9 @@
 namespace dlaf_b200 {
 
 namespace {
+// default fp64 bulk-update engine when DLAF_B200_D_BULK is not set
+constexpr bool kOzakiDefault = false;
+
 inline int cnt_tiles(long g_end, int r, int grid) {
   // number of global tile indices g in [0, g_end) with g % grid == r
   return g_end > r ? static_cast<int>((g_end - r + grid - 1) / grid) : 0;
@@ -62,6 +65,18 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
   DLAF_CUDA_CHECK(cudaMalloc(&d_info_, sizeof(int)));
   DLAF_CUDA_CHECK(cudaMallocHost(&h_info_, sizeof(int)));
   *h_info_ = 0;
+  if constexpr (std::is_same_v<T, double>) {
+    // DLAF_B200_D_BULK = ozaki | dmma : fp64 trailing update on tcgen05 (exact int8 slice products) or on DMMA
+    const char* e = std::getenv("DLAF_B200_D_BULK");
+    const bool want = (e != nullptr) ? (std::string(e) == "ozaki") : kOzakiDefault;
+    use_ozaki_ = want && nt_ > 1 && ltr_ > 0 && ltc_ > 0 && nbp_ <= 512;
+    if (use_ozaki_)
+      for (int i = 0; i < 2; ++i) {
+        osplit_[i].allocate(static_cast<long>(ltr_) * nbp_, nbp_);
+        if (geo_.P > 1)
+          osplitT_[i].allocate(static_cast<long>(ltc_) * nbp_, nbp_);
+      }
+  }
   if constexpr (std::is_same_v<T, float>) {
     // DLAF_B200_S_SIMT=1 keeps the SIMT fp32 kernel everywhere (A/B measurements)
     use_tf32_ = nt_ > 1 && ltr_ > 0 && ltc_ > 0 && std::getenv("DLAF_B200_S_SIMT") == nullptr;
@@ -112,6 +127,12 @@ PotrfEngine<T>::~PotrfEngine() {
     for (int i = 0; i < 2; ++i) {
       split_[i].release();
       splitT_[i].release();
+    }
+  }
+  if constexpr (std::is_same_v<T, double>) {
+    for (int i = 0; i < 2; ++i) {
+      osplit_[i].release();
+      osplitT_[i].release();
     }
   }
   cudaFree(own_slab_);
@@ -399,6 +420,12 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
           ++launches_;
         }
       }
+      if constexpr (std::is_same_v<T, double>) {
+        if (use_ozaki_ && k < nt_ - 1 && P * Q == 1) {
+          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sH_);
+          ++launches_;
+        }
+      }
     }
   }
 
@@ -441,6 +468,18 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       }
       if (P > 1 && ltc_ - lj1 > 0) {
         splitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sH_, nbp_, static_cast<long>(tsz));
+        ++launches_;
+      }
+    }
+  }
+  if constexpr (std::is_same_v<T, double>) {
+    if (use_ozaki_ && k < nt_ - 1 && P * Q > 1) {
+      if (mt > 0) {
+        osplit_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sH_, nbp_, static_cast<long>(tsz));
+        ++launches_;
+      }
+      if (P > 1 && ltc_ - lj1 > 0) {
+        osplitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sH_, nbp_, static_cast<long>(tsz));
         ++launches_;
       }
     }
@@ -533,6 +572,18 @@ void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows
       return;
     }
   }
+  if constexpr (std::is_same_v<T, double>) {
+    if (use_ozaki_) {
+      const long a_row = static_cast<long>(ri0 - li1) * nbp_;
+      if (P > 1)
+        launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplitT_[slot], static_cast<long>(cj0 - lj1) * nbp_, st);
+      else
+        launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplit_[slot], static_cast<long>(gj0 - (k + 1)) * nbp_, st,
+                             static_cast<long>(Q) * nbp_);
+      ++launches_;
+      return;
+    }
+  }
   gemm(a, st);
 }
 
@@ -597,7 +648,7 @@ int PotrfEngine<T>::chunk_of(int lj) const {
 template <class T>
 void PotrfEngine<T>::wait_bulk(int k, int lj, cudaStream_t st) {
   const int nc = nchunks();
-  if (geo_.P * geo_.Q > 1 || lj < 0 || use_tf32_) {
+  if (geo_.P * geo_.Q > 1 || lj < 0 || split_panels()) {
     // distributed / split panels: the panel workspaces of step k are shared by all chunks -> wait for all
     for (int c = 0; c < nc; ++c)
       DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[2 * c + k % 2], 0));

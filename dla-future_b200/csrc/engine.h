@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "gemm_args.h"
+#include "gemm_ozaki.h"
 #include "gemm_tf32.h"
 #include "layout.cuh"
 #include "potrf_tile.cuh"
@@ -152,6 +153,11 @@ private:
   bool use_tf32_ = false;
   Tf32Split split_[2];   // column panel (rows = my local panel rows)
   Tf32Split splitT_[2];  // transposed panel (P > 1 only: tiles (j,k) for my local columns j)
+  // fp64 only: tcgen05 int8 Ozaki-scheme trailing update (gemm_ozaki_i8.cu) — same life cycle as the TF32 splits
+  bool use_ozaki_ = false;
+  OzakiSplit osplit_[2];
+  OzakiSplit osplitT_[2];
+  bool split_panels() const { return use_tf32_ || use_ozaki_; }
   int* d_info_ = nullptr;
   int* h_info_ = nullptr;
   long launches_ = 0;

@@ -1,0 +1,411 @@
+// fp64 trailing update on tcgen05 via exact int8 slice products (Ozaki scheme), see gemm_ozaki.h.
+//
+//   C(MxN, fp64, column-major) += alpha * A(MxK) B(NxK)^T          alpha = +-1, lower-triangular tile mask
+//
+// Replaces the cublasDgemm / cublasDsyrk tile calls of the reference's trailing update
+// (include/dlaf/factorization/cholesky/impl.h:69-94, include/dlaf/blas/tile.h:249-304) for the bulk (~95 % of the
+// flops) of DPOTRF, above the 37 TFLOP/s DMMA/DFMA roofline of B200: 36 int8 MMAs (t + u < 8) per fp64 product
+// at the int8 tensor rate.
+//
+// Operands: OzakiSplit (split_i8_kernel below): 8 int8 digit planes per panel, K-major, + one power-of-two scale
+// per row. CTA = one 128 x 64 tile of C; TMEM holds the 8 anti-diagonal group accumulators (8 x 64 columns of int32
+// = all 512 columns). 6 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// Pipeline: 2 stages x {8 A planes (128 rows x 64 k), 8 B planes (64 rows x 64 k)} = 96 KB per stage, loaded by two
+// 3-D TMA boxes (k, row, plane) in SWIZZLE_64B K-major UMMA layout; 72 tcgen05.mma.kind::i8 (M128 N64 K32) per
+// stage; full/empty mbarriers, tcgen05.commit releases a stage / signals the epilogue. Every wait is bounded.
+// Epilogue: per row (= TMEM lane) and 8 columns at a time, the 8 int32 group sums are folded in fp64 by Horner
+// (smallest group first), scaled by 2^(e_row + e_col - 14) and added to C with coalesced column accesses.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.h"
+#include "gemm_args.h"
+#include "gemm_ozaki.h"
+
+namespace dlaf_b200 {
+
+namespace {
+
+constexpr int S = kOzakiSlices;
+constexpr int OBM = 128, OBN = 64, OBK = 64 /* int8 k per stage */, OSTAGES = 2;
+constexpr int A_PLANE_BYTES = OBM * OBK;  // 8 KB
+constexpr int B_PLANE_BYTES = OBN * OBK;  // 4 KB
+constexpr int A_STAGE_BYTES = S * A_PLANE_BYTES;
+constexpr int B_STAGE_BYTES = S * B_PLANE_BYTES;
+constexpr int OSTAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 96 KB
+constexpr int OTHREADS = 192;
+constexpr int OSMEM_BYTES = OSTAGES * OSTAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers + column scales*/;
+constexpr uint32_t kTmemCols = 512;  // group g at columns [64 g, 64 g + 64)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done)
+      return;
+    if (spin > (1u << 26))
+      __trap();  // a broken pipeline must not hang the device
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_64B, 64-byte rows, 8-row groups
+  // 512 bytes apart. start [0,14) (>>4), LBO [16,30) = 1 (unused for swizzled K-major), SBO [32,46) = 512 >> 4,
+  // version [46,48) = 1 (Blackwell), layout [61,64) = 4 (SWIZZLE_64B).
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+// kind::i8: D = S32 (c_format 2), A = B = signed 8 bit (format 1), both K-major, M = 128, N = 64
+// (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((OBN >> 3) << 17) | ((OBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDescI8), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+struct OzakiParams {
+  double* C;
+  long ldc;
+  int K;         // int8 k per row (= kdim)
+  double alpha;  // +-1
+  GemmArgsT<double> g;  // mask / geometry (A, B, C pointers of g are unused here)
+  int a_row, b_row;     // row of A(0,:) / B(0,:) inside the split arrays
+  int nbp;              // tile edge
+  int b_tile_rows;      // rows of the B split array between consecutive tiles (== nbp when contiguous)
+  const double* scale_a;
+  const double* scale_b;
+};
+
+__global__ void __launch_bounds__(OTHREADS, 1)
+    gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const OzakiParams p) {
+  const int row0 = blockIdx.x * OBM, col0 = blockIdx.y * OBN;
+  long grow0, gcol0;
+  const int cls = classify_tile(p.g, row0, col0, OBM, OBN, grow0, gcol0);
+  if (cls == 0)
+    return;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + OSTAGES * OSTAGE_BYTES);
+  uint64_t* empty = full + OSTAGES;
+  uint64_t* tmem_full = empty + OSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  double* col_scale = reinterpret_cast<double*>(tiles + OSTAGES * OSTAGE_BYTES + 128);  // OBN doubles
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.K / OBK;
+  const int brow = p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < OSTAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mB)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    const int e = threadIdx.x - 64;  // 0..127
+    if (e < OBN)
+      col_scale[e] = p.scale_b[brow + e];
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % OSTAGES;
+        const uint32_t ph = (kb / OSTAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], OSTAGE_BYTES);
+        uint8_t* st = tiles + s * OSTAGE_BYTES;
+        tma_load_3d(st, &mA, &full[s], kb * OBK, p.a_row + row0, 0);
+        tma_load_3d(st + A_STAGE_BYTES, &mB, &full[s], kb * OBK, brow, 0);
+      }
+    }
+  }
+  else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % OSTAGES;
+        const uint32_t ph = (kb / OSTAGES) & 1;
+        mbar_wait(&full[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t stA = smem_u32(tiles + s * OSTAGE_BYTES);
+        const uint32_t stB = stA + A_STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < OBK / 32; ++ks) {
+          const uint64_t adv = static_cast<uint64_t>((ks * 32) >> 4);  // 32 int8 = 32 bytes along K inside the swizzle atom
+#pragma unroll
+          for (int t = 0; t < S; ++t) {
+            const uint64_t ad = make_kmajor_sw64_desc(stA + t * A_PLANE_BYTES) + adv;
+#pragma unroll
+            for (int u = 0; u < S - t; ++u) {
+              const uint64_t bd = make_kmajor_sw64_desc(stB + u * B_PLANE_BYTES) + adv;
+              // digit planes t (A) and u (B) contribute to group g = t + u; the first product of every group
+              // (kb = ks = t = 0) overwrites the accumulator
+              umma_i8(tmem_base + static_cast<uint32_t>((t + u) * OBN), ad, bd, (kb | ks | t) != 0);
+            }
+          }
+        }
+        umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full);  // accumulators complete
+    }
+  }
+  else {
+    // ===== epilogue: warps 2..5, TMEM lanes 32*(warp%4) .. +31 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row of the tile held by this thread
+    const double row_scale = p.scale_a[p.a_row + row0 + r] * p.alpha * 0x1p-14;
+    double* Cg = p.C + row0 + r + static_cast<long>(col0) * p.ldc;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c0 = 0; c0 < OBN; c0 += 8) {
+      double cv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool on = (cls == 1) || (grow0 + r >= gcol0 + c0 + j);
+        cv[j] = on ? Cg[static_cast<long>(c0 + j) * p.ldc] : 0.0;
+      }
+      int acc[S][8];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+#pragma unroll
+      for (int g = 0; g < S; ++g)
+        tmem_ld8(taddr + static_cast<uint32_t>(g * OBN), acc[g]);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (cls != 1 && (grow0 + r < gcol0 + c0 + j))
+          continue;
+        double v = static_cast<double>(acc[S - 1][j]);
+#pragma unroll
+        for (int g = S - 2; g >= 0; --g)
+          v = fma(v, 0x1p-7, static_cast<double>(acc[g][j]));
+        Cg[static_cast<long>(c0 + j) * p.ldc] = fma(v, row_scale * col_scale[c0 + j], cv[j]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// x (rows x kdim, column-major with leading dimension ld) -> 8 int8 digit planes (K-major) + 2^e per row.
+// Block = 32 rows x 8 k-groups (256 threads); thread (r, kg) owns k = kg, kg + 8, ... of its row in registers
+// (loads of a warp = 32 consecutive rows of one column: coalesced).
+template <int KDIM>
+__global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict__ x, long ld, int rows,
+                                                       signed char* __restrict__ q, long plane_stride,
+                                                       double* __restrict__ scale, int tile_rows, long tile_stride) {
+  constexpr int KG = 8, PER = KDIM / KG;  // k values per thread, contiguous chunk [kg * PER, (kg + 1) * PER)
+  __shared__ double smax[KG][33];
+  const int tr = threadIdx.x & 31, kg = threadIdx.x >> 5;
+  const int r = blockIdx.x * 32 + tr;
+  const bool live = r < rows;
+  const long roff = live ? (tile_stride ? (r / tile_rows) * tile_stride + r % tile_rows : r) : 0;
+  double v[PER];
+  double m = 0.0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    v[i] = live ? x[roff + static_cast<long>(kg * PER + i) * ld] : 0.0;
+    m = fmax(m, fabs(v[i]));
+  }
+  smax[kg][tr] = m;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < KG; ++i)
+    m = fmax(m, smax[i][tr]);
+  // |v| * 2^-e <= 0.5   (e = ilogb(max) + 2);   all-zero (or non-finite) rows: e = 0
+  int e = 0;
+  if (m > 0.0 && m < 1.0e300)
+    e = ilogb(m) + 2;
+  e = e < -1000 ? -1000 : (e > 1000 ? 1000 : e);
+  const double down = __hiloint2double((1023 - e) << 20, 0);  // 2^-e
+  if (kg == 0 && live)
+    scale[r] = __hiloint2double((1023 + e) << 20, 0);  // 2^e
+#pragma unroll
+  for (int i = 0; i < PER; ++i)
+    v[i] *= down;
+  if (!live)
+    return;
+  signed char* dst = q + static_cast<long>(r) * KDIM + kg * PER;
+#pragma unroll 1
+  for (int t = 0; t < S; ++t) {
+    uint32_t w[PER / 4];
+#pragma unroll
+    for (int i = 0; i < PER; i += 4) {
+      uint32_t pack = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double s = v[i + b] * 128.0;
+        const int d = __double2int_rn(s);  // |d| <= 64
+        v[i + b] = s - static_cast<double>(d);
+        pack |= (static_cast<uint32_t>(d) & 0xFFu) << (8 * b);
+      }
+      w[i / 4] = pack;
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + t * plane_stride);
+#pragma unroll
+    for (int i = 0; i < PER / 16; ++i)
+      o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+  }
+}
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    DLAF_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr));
+    DLAF_B200_ASSERT(f != nullptr && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    return reinterpret_cast<EncodeFn>(f);
+  }();
+  return fn;
+}
+
+}  // namespace
+
+void OzakiSplit::allocate(long rows_max, int kdim_) {
+  release();
+  rows = rows_max;
+  kdim = kdim_;
+  DLAF_B200_ASSERT(kdim % 128 == 0, "Ozaki split: k must be a multiple of 128");
+  DLAF_CUDA_CHECK(cudaMalloc(&q, static_cast<size_t>(S) * rows * kdim));
+  DLAF_CUDA_CHECK(cudaMalloc(&scale, sizeof(double) * rows));
+  DLAF_CUDA_CHECK(cudaMemset(q, 0, static_cast<size_t>(S) * rows * kdim));
+  // 3-D maps: dim0 = k (contiguous, bytes), dim1 = row, dim2 = digit plane; box = 64 k x {128, 64} rows x 8 planes;
+  // 64-byte swizzle
+  const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(S)};
+  const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(kdim) * static_cast<cuuint64_t>(rows)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  for (int i = 0; i < 2; ++i) {
+    const cuuint32_t box[3] = {OBK, static_cast<cuuint32_t>(i == 0 ? OBM : OBN), S};
+    CUtensorMap* m = reinterpret_cast<CUtensorMap*>(i == 0 ? map_a : map_b);
+    const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, q, dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DLAF_B200_ASSERT(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  }
+}
+
+void OzakiSplit::release() {
+  cudaFree(q);
+  cudaFree(scale);
+  q = nullptr;
+  scale = nullptr;
+}
+
+void OzakiSplit::split(const double* x, long ld, long nrows, cudaStream_t s, int tile_rows, long tile_stride) {
+  DLAF_B200_ASSERT(nrows <= rows, "split buffer too small");
+  if (nrows <= 0)
+    return;
+  const unsigned grid = static_cast<unsigned>((nrows + 31) / 32);
+  const long plane_stride = rows * static_cast<long>(kdim);
+  const int tr = tile_rows > 0 ? tile_rows : 1;
+  switch (kdim) {
+    case 128: split_i8_kernel<128><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
+    case 256: split_i8_kernel<256><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
+    case 384: split_i8_kernel<384><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
+    case 512: split_i8_kernel<512><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
+    default: DLAF_B200_ASSERT(false, "Ozaki split: unsupported k (128, 256, 384 or 512)");
+  }
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+
+static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+
+void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long a_row, const OzakiSplit& sb, long b_row,
+                          cudaStream_t stream, long b_tile_rows) {
+  if (a.M <= 0 || a.N <= 0)
+    return;
+  DLAF_B200_ASSERT(a.M % OBM == 0 && a.N % OBN == 0 && a.K % OBK == 0 && a.K == sa.kdim && a.K == sb.kdim,
+                   "ozaki gemm shape");
+  DLAF_B200_ASSERT((a.alpha == 1.0 || a.alpha == -1.0) && a.beta == 1.0, "ozaki gemm: C += +-A B^T only");
+  static bool configured = false;
+  if (!configured) {
+    DLAF_CUDA_CHECK(cudaFuncSetAttribute(gemm_ozaki_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OSMEM_BYTES));
+    configured = true;
+  }
+  OzakiParams p;
+  p.C = a.C;
+  p.ldc = a.ldc;
+  p.K = a.K;
+  p.alpha = a.alpha;
+  p.g = a;
+  p.a_row = static_cast<int>(a_row);
+  p.b_row = static_cast<int>(b_row);
+  p.nbp = a.nbp;
+  p.b_tile_rows = static_cast<int>(b_tile_rows > 0 ? b_tile_rows : a.nbp);
+  p.scale_a = sa.scale;
+  p.scale_b = sb.scale;
+  dim3 grid(a.M / OBM, a.N / OBN);
+  gemm_ozaki_i8_kernel<<<grid, OTHREADS, OSMEM_BYTES, stream>>>(*reinterpret_cast<const CUtensorMap*>(sa.map_a),
+                                                                 *reinterpret_cast<const CUtensorMap*>(sb.map_b), p);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace dlaf_b200

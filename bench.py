@@ -286,29 +286,52 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             log(f"[bench] residual check skipped: {e}")
 
-    # ---- roofline of the dominant kernel (bulk trailing update, DMMA GEMM)
-    peak = pkg.measure_fp64_tensor_peak_tflops()
-    achieved = (prof_fl / (prof_ms * 1e-3) / 1e12) if prof_ms > 0 else None
+    # ---- roofline of the dominant kernel (bulk trailing update on stream L)
+    # fp64 engine (DLAF_B200_D_BULK): "ozaki" (default) = exact int8 digit products on tcgen05, 36 int8 MACs per fp64 MAC,
+    # bounded by the int8 tensor pipe; "dmma" = native fp64 DMMA, bounded by the fp64 tensor pipe.
+    engine = os.environ.get("DLAF_B200_D_BULK", "ozaki")
+    peak64 = pkg.measure_fp64_tensor_peak_tflops()
+    achieved64 = (prof_fl / (prof_ms * 1e-3) / 1e12) if prof_ms > 0 else None
+    cap_file = "r01_ncu_ozaki_bulk.json" if engine == "ozaki" else "r01_ncu_gemm_bulk_final.json"
     traffic, traffic_note = None, None
     try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (one launch)
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm_bulk_final.json")) as f:
+        with open(os.path.join(ROOT, "profiles", cap_file)) as f:
             cap = json.load(f)
         traffic = cap["dram_bytes_read"] + cap["dram_bytes_write"]
         traffic_note = (f"ncu capture of ONE launch: {cap['launch']}; algorithmic bytes of that launch "
-                        f"{cap['algorithmic_bytes']} (C lower triangle read+write + panel), DMMA pipe active "
-                        f"{cap['dmma_pipe_active_pct']} %, L2 hit {cap['l2_hit_pct']} %")
+                        f"{cap['algorithmic_bytes']}; {cap.get('note', '')}")
     except Exception:
         pass
-    roofline = {
-        "kernel": "gemm_nt_f64_kernel<GemmCfg<64,64,16,3,4,2,2>> (bulk trailing update, stream L)", "bound": "tensor",
-        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-        "traffic": traffic, "traffic_note": traffic_note,
-        "peak_source": "measured now on this GPU: DMMA.8x8x4 issue-rate microbenchmark (dlaf_b200_measure_fp64_tensor_peak_tflops); "
-                       "MEASURED_PEAKS.json holds no fp64 figure (bf16 cuBLAS + HBM copy only); nominal B200 fp64 = 40 TFLOP/s",
-        "launches_timed": prof_n, "critical_path_ms_last_step": chain, "kernel_ms_per_step": prof_ms / K if K else None,
+    if engine == "ozaki":
+        peak8 = pkg.measure_int8_tensor_peak_tops()
+        achieved8 = achieved64 * 36.0 if achieved64 else None
+        roofline = {
+            "kernel": "gemm_ozaki_i8_kernel (bulk trailing update, stream L): fp64 C -= A B^T as 36 exact int8 tcgen05 MMAs",
+            "bound": "tensor", "achieved": achieved8, "peak": peak8, "unit": "TFLOP/s",
+            "frac": (achieved8 / peak8) if achieved8 else None,
+            "unit_note": "int8 tensor-core tera-ops/s (1 MAC = 2 ops); algorithmic ops per launch = 36 x the fp64 flops of "
+                         "the update (8 x 7-bit digits, digit pairs t + u < 8)",
+            "fp64_equivalent_tflops": achieved64, "fp64_tensor_peak_tflops": peak64,
+            "frac_of_fp64_tensor_roofline": (achieved64 / peak64) if achieved64 else None,
+            "traffic": traffic, "traffic_note": traffic_note,
+            "peak_source": "measured now on this GPU: tcgen05.mma.kind::i8 M128 N256 K32 issue-rate microbenchmark "
+                           "(dlaf_b200_measure_int8_tensor_peak_tops); MEASURED_PEAKS.json holds bf16 (1639 TF/s burst) and "
+                           "HBM only; nominal B200 int8 dense = 4500 TOP/s. fp64 tensor (DMMA) peak measured the same way.",
+        }
+    else:
+        roofline = {
+            "kernel": "gemm_nt_f64_kernel<GemmCfg<64,64,16,3,4,2,2>> (bulk trailing update, stream L)", "bound": "tensor",
+            "achieved": achieved64, "peak": peak64, "unit": "TFLOP/s", "frac": (achieved64 / peak64) if achieved64 else None,
+            "traffic": traffic, "traffic_note": traffic_note,
+            "peak_source": "measured now on this GPU: DMMA.8x8x4 issue-rate microbenchmark (dlaf_b200_measure_fp64_tensor_peak_tflops); "
+                           "MEASURED_PEAKS.json holds no fp64 figure (bf16 cuBLAS + HBM copy only); nominal B200 fp64 = 40 TFLOP/s",
+        }
+    roofline.update({
+        "engine": engine, "launches_timed": prof_n, "critical_path_ms_last_step": chain,
+        "kernel_ms_per_step": prof_ms / K if K else None,
         "kernel_share_of_step": (prof_ms / K) / ms_per_step if K else None,
-        "whole_potrf_frac_of_peak": value / 1e3 / (peak * world),
-    }
+        "whole_potrf_frac_of_fp64_tensor_peak": value / 1e3 / (peak64 * world),
+    })
     del d_work
 
     # ---- end to end through the reference-facing C ABI with HOST buffers (H2D + D2H inside)
@@ -375,6 +398,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
+            "dtype_note": ("fp64 in, fp64 out; panels (POTRF/TRSM) in native fp64 DMMA; trailing update = exact int8 digit products "
+                           "(8 x 7-bit digits per operand, int32 accumulation, fp64 recombination) whose error is BELOW a native "
+                           "fp64 GEMM (tools/gpu_ozaki_test: 2.9e-17 vs 3.9e-16 of sum|a||b|)") if os.environ.get("DLAF_B200_D_BULK", "ozaki") == "ozaki" else "native fp64 (DMMA)",
             "config": {"workload": f"fp64 POTRF N={n} nb={nb} uplo=L, grid {P}x{Q} (ColumnMajor), device-resident, in place",
                        "input": "set_random_hermitian_positive_definite (miniapp generator), restored before every step",
                        "l2": "matrix (%.1f GB per GPU) is larger than L2; every step starts from a fresh copy" % (lr * lc * 8 / 1e9),

@@ -34,7 +34,7 @@ C_API_SYMBOLS = [
     *[f"dlaf_b200_set_random_hermitian_positive_definite_{t}" for t in "sdcz"],
     *[f"dlaf_b200_check_cholesky_{t}" for t in "sdcz"], "dlaf_b200_grid_barrier",
     "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info",
-    "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops",
+    "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops", "dlaf_b200_measure_int8_tensor_peak_tops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
 ]
 
@@ -144,6 +144,7 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_read_chain_profile.argtypes = [ci, ctypes.POINTER(ctypes.c_double)]
     L.dlaf_b200_read_chain_profile.restype = None
     L.dlaf_b200_measure_fp64_tensor_peak_tflops.restype = ctypes.c_double
+    L.dlaf_b200_measure_int8_tensor_peak_tops.restype = ctypes.c_double
     L.dlaf_b200_grid_info.argtypes = [ci, ctypes.POINTER(ci)]
     L.dlaf_b200_grid_info.restype = None
     L.dlaf_b200_local_rows.argtypes = [ci, DLAF_descriptor]
@@ -288,6 +289,11 @@ def read_chain_profile(ctx: int):
 
 def measure_fp64_tensor_peak_tflops() -> float:
     return lib().dlaf_b200_measure_fp64_tensor_peak_tflops()
+
+
+def measure_int8_tensor_peak_tops() -> float:
+    """tcgen05.mma.kind::i8 issue-rate peak of this GPU in TOP/s (roofline of the Ozaki-scheme fp64 update)."""
+    return lib().dlaf_b200_measure_int8_tensor_peak_tops()
 
 
 def set_random_hermitian_positive_definite(ctx: int, a: np.ndarray, n: int, nb: int, isrc: int = 0,

@@ -13,7 +13,7 @@ namespace dlaf_b200 {
 
 namespace {
 // default fp64 bulk-update engine when DLAF_B200_D_BULK is not set
-constexpr bool kOzakiDefault = false;
+constexpr bool kOzakiDefault = true;
 
 inline int cnt_tiles(long g_end, int r, int grid) {
   // number of global tile indices g in [0, g_end) with g % grid == r

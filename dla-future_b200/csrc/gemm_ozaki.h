@@ -41,4 +41,8 @@ struct OzakiSplit {
 void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long a_row, const OzakiSplit& sb, long b_row,
                           cudaStream_t stream, long b_tile_rows = 0);
 
+// Measurement aid (tools/): device buffer of 4096 x 8 clock64 stamps (first 4096 CTAs of a launch); nullptr = off.
+// stamps: 0 entry, 1 set-up done, 2 first stage landed, 3 last MMA issued, 4 accumulators complete, 5 epilogue done, 6 exit
+void ozaki_set_clock_trace(long long* dev_buffer);
+
 }  // namespace dlaf_b200

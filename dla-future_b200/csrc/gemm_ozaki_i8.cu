@@ -10,10 +10,11 @@
 // Operands: OzakiSplit (split_i8_kernel below): 8 int8 digit planes per panel, K-major, + one power-of-two scale
 // per row. CTA = one 128 x 64 tile of C; TMEM holds the 8 anti-diagonal group accumulators (8 x 64 columns of int32
 // = all 512 columns). 6 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4). Each CTA handles a few
+// consecutive tiles (DLAF_B200_OZAKI_TPC).
 // Pipeline: 2 stages x {8 A planes (128 rows x 64 k), 8 B planes (64 rows x 64 k)} = 96 KB per stage, loaded by two
-// 3-D TMA boxes (k, row, plane) in SWIZZLE_64B K-major UMMA layout; 72 tcgen05.mma.kind::i8 (M128 N64 K32) per
-// stage; full/empty mbarriers, tcgen05.commit releases a stage / signals the epilogue. Every wait is bounded.
+// 3-D TMA boxes (k, row, plane) in SWIZZLE_64B K-major UMMA layout; 24 tcgen05.mma.kind::i8 (M128, N up to 256, K32) per
+// stage (one instruction covers up to 4 digit-plane pairs, see the issuer loop); full/empty mbarriers, tcgen05.commit releases a stage / signals the epilogue. Every wait is bounded.
 // Epilogue: per row (= TMEM lane) and 8 columns at a time, the 8 int32 group sums are folded in fp64 by Horner
 // (smallest group first), scaled by 2^(e_row + e_col - 14) and added to C with coalesced column accesses.
 #include <cuda.h>
@@ -38,8 +39,10 @@ constexpr int B_PLANE_BYTES = OBN * OBK;  // 4 KB
 constexpr int A_STAGE_BYTES = S * A_PLANE_BYTES;
 constexpr int B_STAGE_BYTES = S * B_PLANE_BYTES;
 constexpr int OSTAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 96 KB
-constexpr int OTHREADS = 192;
-constexpr int OSMEM_BYTES = OSTAGES * OSTAGE_BYTES + 1024 /*alignment slack*/ + 1024 /*barriers + column scales*/;
+constexpr int OEPI_WARPS = 8;
+constexpr int OTHREADS = 64 + 32 * OEPI_WARPS;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int OSMEM_BYTES = OSTAGES * OSTAGE_BYTES + 1024 /*alignment slack*/ + 2048 /*barriers + column scales*/;
+constexpr int kRowChunk = 64;  // row tiles per rasterization chunk
 constexpr uint32_t kTmemCols = 512;  // group g at columns [64 g, 64 g + 64)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -88,14 +91,16 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
 }
 // kind::i8: D = S32 (c_format 2), A = B = signed 8 bit (format 1), both K-major, M = 128, N = 64
 // (cute::UMMA::InstrDescriptor bit layout)
-constexpr uint32_t kInstrDescI8 = (2u << 4) | (1u << 7) | (1u << 10) | ((OBN >> 3) << 17) | ((OBM >> 4) << 24);
+__host__ __device__ constexpr uint32_t instr_desc_i8(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(OBM >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDescI8), "r"(accumulate)
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -108,6 +113,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
                : "memory");
 }
 
+// Measurement aid: when non-null, CTAs with linear index < kDbgCtas record clock64() at 7 phase boundaries.
+__device__ long long* g_ozaki_clock_trace = nullptr;
+constexpr int kDbgCtas = 4096;
+#define OZ_TRACE(slot)                                                        \
+  do {                                                                        \
+    if (trace)                                                                \
+      trace[static_cast<long>(lin) * 8 + (slot)] = clock64();                 \
+  } while (0)
+
 struct OzakiParams {
   double* C;
   long ldc;
@@ -119,27 +133,60 @@ struct OzakiParams {
   int b_tile_rows;      // rows of the B split array between consecutive tiles (== nbp when contiguous)
   const double* scale_a;
   const double* scale_b;
+  int gx, gy;          // tile grid (M / 128, N / 64)
+  int tiles_per_cta;
 };
+
+// signed 64-bit integer (|v| < 2^51) -> double, exactly, on the integer + fp64-add pipes (no I2F)
+__device__ __forceinline__ double i64_to_f64_exact(long long v) {
+  return __longlong_as_double(0x4330000000000000LL + (v + (1LL << 51))) - 0x1.8p52;
+}
 
 __global__ void __launch_bounds__(OTHREADS, 1)
     gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const OzakiParams p) {
-  const int row0 = blockIdx.x * OBM, col0 = blockIdx.y * OBN;
-  long grow0, gcol0;
-  const int cls = classify_tile(p.g, row0, col0, OBM, OBN, grow0, gcol0);
-  if (cls == 0)
-    return;
-
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + OSTAGES * OSTAGE_BYTES);
   uint64_t* empty = full + OSTAGES;
   uint64_t* tmem_full = empty + OSTAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  double* col_scale = reinterpret_cast<double*>(tiles + OSTAGES * OSTAGE_BYTES + 128);  // OBN doubles
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  double* col_scale = reinterpret_cast<double*>(tiles + OSTAGES * OSTAGE_BYTES + 128);  // 2 x OBN doubles (tile parity)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned lin = blockIdx.x;
+  long long* trace = (g_ozaki_clock_trace != nullptr && lin < kDbgCtas) ? g_ozaki_clock_trace : nullptr;
+  if (threadIdx.x == 0)
+    OZ_TRACE(0);
   const int KB = p.K / OBK;
-  const int brow = p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp;
+  // This CTA owns the tiles with linear index [first, last) (row tile fastest: consecutive tiles share their B rows).
+  // A bounded number of tiles per CTA keeps the CTAs short-lived, so the high-priority panel kernels of the POTRF
+  // schedule still get SMs as CTAs retire, while set-up, TMEM allocation and the first TMA loads of a tile are
+  // amortised / overlapped with the previous tile's epilogue.
+  const int first = blockIdx.x * p.tiles_per_cta;
+  const int last = min(first + p.tiles_per_cta, p.gx * p.gy);
+  // Rasterization: row tiles in chunks of kRowChunk (8192 rows = 32 MB of A digit planes, L2 resident), all column
+  // tiles of a chunk before the next chunk, row tile fastest inside a column — so the A planes are read from HBM
+  // once per chunk instead of once per column tile when the panel (132 MB at 32768 rows) exceeds L2.
+  auto tile_of = [&](int l, int& row0, int& col0, long& grow0, long& gcol0) {
+    const int per_chunk = kRowChunk * p.gy;
+    const int chunk = l / per_chunk, rem = l - chunk * per_chunk;
+    const int rows_here = min(kRowChunk, p.gx - chunk * kRowChunk);
+    const int by = rem / rows_here, bx = chunk * kRowChunk + rem - by * rows_here;
+    row0 = bx * OBM;
+    col0 = by * OBN;
+    return classify_tile(p.g, row0, col0, OBM, OBN, grow0, gcol0);
+  };
+  {
+    bool any = false;
+    for (int l = first; l < last && !any; ++l) {
+      int r0, c0;
+      long gr, gc;
+      any = tile_of(l, r0, c0, gr, gc) != 0;
+    }
+    if (!any)
+      return;  // uniform across the CTA
+  }
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < OSTAGES; ++s) {
@@ -147,6 +194,7 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       mbar_init(&empty[s], 1);
     }
     mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, OEPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mB)) : "memory");
@@ -155,11 +203,6 @@ __global__ void __launch_bounds__(OTHREADS, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) {
-    const int e = threadIdx.x - 64;  // 0..127
-    if (e < OBN)
-      col_scale[e] = p.scale_b[brow + e];
-  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -167,88 +210,147 @@ __global__ void __launch_bounds__(OTHREADS, 1)
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer =====
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % OSTAGES;
-        const uint32_t ph = (kb / OSTAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], OSTAGE_BYTES);
-        uint8_t* st = tiles + s * OSTAGE_BYTES;
-        tma_load_3d(st, &mA, &full[s], kb * OBK, p.a_row + row0, 0);
-        tma_load_3d(st + A_STAGE_BYTES, &mB, &full[s], kb * OBK, brow, 0);
+      // ===== TMA producer: runs ahead into the next tile while the epilogue of the current one is busy =====
+      int it = 0;  // stage uses so far
+      for (int l = first; l < last; ++l) {
+        int row0, col0;
+        long gr, gc;
+        if (tile_of(l, row0, col0, gr, gc) == 0)
+          continue;
+        const int brow = p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % OSTAGES;
+          const uint32_t ph = (it / OSTAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], OSTAGE_BYTES);
+          uint8_t* st = tiles + s * OSTAGE_BYTES;
+          tma_load_3d(st, &mA, &full[s], kb * OBK, p.a_row + row0, 0);
+          tma_load_3d(st + A_STAGE_BYTES, &mB, &full[s], kb * OBK, brow, 0);
+        }
       }
     }
   }
   else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % OSTAGES;
-        const uint32_t ph = (kb / OSTAGES) & 1;
-        mbar_wait(&full[s], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t stA = smem_u32(tiles + s * OSTAGE_BYTES);
-        const uint32_t stB = stA + A_STAGE_BYTES;
+      OZ_TRACE(1);
+      int it = 0, tcount = 0;
+      for (int l = first; l < last; ++l) {
+        int row0, col0;
+        long gr, gc;
+        if (tile_of(l, row0, col0, gr, gc) == 0)
+          continue;
+        if (tcount > 0) {  // the epilogue must have drained the accumulators of the previous tile
+          mbar_wait(tmem_empty, (tcount - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % OSTAGES;
+          const uint32_t ph = (it / OSTAGES) & 1;
+          mbar_wait(&full[s], ph);
+          if (it == 0)
+            OZ_TRACE(2);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t stA = smem_u32(tiles + s * OSTAGE_BYTES);
+          const uint32_t stB = stA + A_STAGE_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < OBK / 32; ++ks) {
-          const uint64_t adv = static_cast<uint64_t>((ks * 32) >> 4);  // 32 int8 = 32 bytes along K inside the swizzle atom
+          for (int ks = 0; ks < OBK / 32; ++ks) {
+            const uint64_t adv = static_cast<uint64_t>((ks * 32) >> 4);  // 32 int8 = 32 bytes along K inside the swizzle atom
 #pragma unroll
-          for (int t = 0; t < S; ++t) {
-            const uint64_t ad = make_kmajor_sw64_desc(stA + t * A_PLANE_BYTES) + adv;
+            for (int t = 0; t < S; ++t) {
+              const uint64_t ad = make_kmajor_sw64_desc(stA + t * A_PLANE_BYTES) + adv;
+              // Digit plane t of A meets planes u = 0 .. 7-t of B; their groups g = t + u sit side by side in TMEM
+              // (64 columns each) and the B planes side by side in shared memory (64 rows each), so ONE instruction
+              // with N = 64 (8 - t) covers them all — split only at the N <= 256 limit of the instruction:
+              // 12 large MMAs per k-step instead of 36 small ones. The first product of every group
+              // (kb = ks = t = 0) overwrites its accumulator.
 #pragma unroll
-            for (int u = 0; u < S - t; ++u) {
-              const uint64_t bd = make_kmajor_sw64_desc(stB + u * B_PLANE_BYTES) + adv;
-              // digit planes t (A) and u (B) contribute to group g = t + u; the first product of every group
-              // (kb = ks = t = 0) overwrites the accumulator
-              umma_i8(tmem_base + static_cast<uint32_t>((t + u) * OBN), ad, bd, (kb | ks | t) != 0);
+              for (int u0 = 0; u0 < S - t; u0 += 4) {
+                const int planes = (S - t - u0) < 4 ? (S - t - u0) : 4;
+                const uint64_t bd = make_kmajor_sw64_desc(stB + u0 * B_PLANE_BYTES) + adv;
+                umma_i8(tmem_base + static_cast<uint32_t>((t + u0) * OBN), ad, bd, instr_desc_i8(planes * OBN), (kb | ks | t) != 0);
+              }
             }
           }
+          umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
         }
-        umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+        if (tcount == 0)
+          OZ_TRACE(3);
+        umma_commit(tmem_full);  // accumulators of this tile complete
+        ++tcount;
       }
-      umma_commit(tmem_full);  // accumulators complete
     }
   }
   else {
-    // ===== epilogue: warps 2..5, TMEM lanes 32*(warp%4) .. +31 =====
-    const int q = warp & 3;
+    // ===== epilogue: 8 warps; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row of the tile held by this thread
-    const double row_scale = p.scale_a[p.a_row + row0 + r] * p.alpha * 0x1p-14;
-    double* Cg = p.C + row0 + r + static_cast<long>(col0) * p.ldc;
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-    for (int c0 = 0; c0 < OBN; c0 += 8) {
-      double cv[8];
+    const int e = threadIdx.x - 64;  // 0..255
+    constexpr int HC = OBN / 2;      // columns per thread
+    int tcount = 0;
+    for (int l = first; l < last; ++l) {
+      int row0, col0;
+      long grow0, gcol0;
+      const int cls = tile_of(l, row0, col0, grow0, gcol0);
+      if (cls == 0)
+        continue;
+      double* cs = col_scale + (tcount & 1) * OBN;
+      if (e < OBN)
+        cs[e] = p.scale_b[p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp + e];
+      const double row_scale = p.scale_a[p.a_row + row0 + r] * p.alpha * 0x1p-35;  // 2^-14 digits, 2^-21 from the fold
+      const int cb = half * HC;
+      double* Cg = p.C + row0 + r + static_cast<long>(col0 + cb) * p.ldc;
+      const long gr = grow0 + r, gc = gcol0 + cb;
+      // The C row segment of this thread is fetched while the MMAs run: after the accumulators complete only TMEM
+      // loads, the integer fold, two exact conversions and the stores remain.
+      double cv[HC];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const bool on = (cls == 1) || (grow0 + r >= gcol0 + c0 + j);
-        cv[j] = on ? Cg[static_cast<long>(c0 + j) * p.ldc] : 0.0;
+      for (int j = 0; j < HC; ++j) {
+        const bool on = (cls == 1) || (gr >= gc + j);
+        cv[j] = on ? Cg[static_cast<long>(j) * p.ldc] : 0.0;
       }
-      int acc[S][8];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // column scales of this tile are in place
+      mbar_wait(tmem_full, tcount & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (threadIdx.x == 64 && tcount == 0)
+        OZ_TRACE(4);
 #pragma unroll
-      for (int g = 0; g < S; ++g)
-        tmem_ld8(taddr + static_cast<uint32_t>(g * OBN), acc[g]);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int c0 = 0; c0 < HC; c0 += 8) {
+        int acc[S][8];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb + c0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (cls != 1 && (grow0 + r < gcol0 + c0 + j))
-          continue;
-        double v = static_cast<double>(acc[S - 1][j]);
+        for (int g = 0; g < S; ++g)
+          tmem_ld8(taddr + static_cast<uint32_t>(g * OBN), acc[g]);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int g = S - 2; g >= 0; --g)
-          v = fma(v, 0x1p-7, static_cast<double>(acc[g][j]));
-        Cg[static_cast<long>(c0 + j) * p.ldc] = fma(v, row_scale * col_scale[c0 + j], cv[j]);
+        for (int j = 0; j < 8; ++j) {
+          if (cls != 1 && (gr < gc + c0 + j))
+            continue;
+          // sum_g acc_g 128^-g = (hi + lo 2^-28) 2^-21 with two exact 46-bit integers
+          const long long hi = (static_cast<long long>(acc[0][j]) << 21) + (static_cast<long long>(acc[1][j]) << 14) +
+                               (static_cast<long long>(acc[2][j]) << 7) + acc[3][j];
+          const long long lo = (static_cast<long long>(acc[4][j]) << 21) + (static_cast<long long>(acc[5][j]) << 14) +
+                               (static_cast<long long>(acc[6][j]) << 7) + acc[7][j];
+          const double v = fma(i64_to_f64_exact(lo), 0x1p-28, i64_to_f64_exact(hi));
+          Cg[static_cast<long>(c0 + j) * p.ldc] = fma(v, row_scale * cs[cb + c0 + j], cv[c0 + j]);
+        }
       }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty)) : "memory");
+      if (threadIdx.x == 64 && tcount == 0)
+        OZ_TRACE(5);
+      ++tcount;
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
+  if (threadIdx.x == 0)
+    OZ_TRACE(6);
 }
 
 // x (rows x kdim, column-major with leading dimension ld) -> 8 int8 digit planes (K-major) + 2^e per row.
@@ -376,6 +478,51 @@ void OzakiSplit::split(const double* x, long ld, long nrows, cudaStream_t s, int
   DLAF_CUDA_CHECK(cudaGetLastError());
 }
 
+namespace {
+// int8 tensor-pipe peak of this device: every SM issues `iters` back-to-back tcgen05.mma.kind::i8 (M128 N256 K32) on
+// one resident shared-memory tile (no loads in the loop) — the roofline denominator of the Ozaki kernel.
+__global__ void __launch_bounds__(64, 1) i8_peak_kernel(int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* done = reinterpret_cast<uint64_t*>(tiles + 24576);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  for (int i = threadIdx.x; i < 24576 / 4; i += 64)
+    reinterpret_cast<uint32_t*>(tiles)[i] = 0x01010101u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy tile writes -> async proxy (UMMA)
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 1 && lane == 0) {
+    const uint64_t ad = make_kmajor_sw64_desc(smem_u32(tiles));
+    const uint64_t bd = make_kmajor_sw64_desc(smem_u32(tiles + 8192));
+    for (int i = 0; i < iters; ++i)
+      umma_i8(tmem_base + ((i & 1) ? 256u : 0u), ad + ((i & 2) ? 2 : 0), bd + ((i & 2) ? 2 : 0), instr_desc_i8(256), i >= 2);
+    umma_commit(done);
+    mbar_wait(done, 0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+}  // namespace
+
+void ozaki_set_clock_trace(long long* dev_buffer) {
+  DLAF_CUDA_CHECK(cudaMemcpyToSymbol(g_ozaki_clock_trace, &dev_buffer, sizeof(dev_buffer)));
+}
+
 static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
 
 void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long a_row, const OzakiSplit& sb, long b_row,
@@ -402,10 +549,47 @@ void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long
   p.b_tile_rows = static_cast<int>(b_tile_rows > 0 ? b_tile_rows : a.nbp);
   p.scale_a = sa.scale;
   p.scale_b = sb.scale;
-  dim3 grid(a.M / OBM, a.N / OBN);
+  p.gx = a.M / OBM;
+  p.gy = a.N / OBN;
+  // DLAF_B200_OZAKI_TPC: tiles per CTA (default 4: ~50 us CTAs)
+  static const int tpc = [] {
+    const char* e = std::getenv("DLAF_B200_OZAKI_TPC");
+    const int v = e ? std::atoi(e) : 4;
+    return v < 1 ? 1 : v;
+  }();
+  p.tiles_per_cta = tpc;
+  const long ntiles = static_cast<long>(p.gx) * p.gy;
+  const unsigned grid = static_cast<unsigned>((ntiles + tpc - 1) / tpc);
   gemm_ozaki_i8_kernel<<<grid, OTHREADS, OSMEM_BYTES, stream>>>(*reinterpret_cast<const CUtensorMap*>(sa.map_a),
                                                                  *reinterpret_cast<const CUtensorMap*>(sb.map_b), p);
   DLAF_CUDA_CHECK(cudaGetLastError());
 }
 
 }  // namespace dlaf_b200
+
+extern "C" double dlaf_b200_measure_int8_tensor_peak_tops(void) {
+  using namespace dlaf_b200;
+  int dev = 0, nsm = 0;
+  DLAF_CUDA_CHECK(cudaGetDevice(&dev));
+  DLAF_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int smem = 24576 + 1024 + 64, iters = 40000;
+  DLAF_CUDA_CHECK(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1;
+  DLAF_CUDA_CHECK(cudaEventCreate(&e0));
+  DLAF_CUDA_CHECK(cudaEventCreate(&e1));
+  i8_peak_kernel<<<nsm, 64, smem>>>(400);
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    DLAF_CUDA_CHECK(cudaEventRecord(e0));
+    i8_peak_kernel<<<nsm, 64, smem>>>(iters);
+    DLAF_CUDA_CHECK(cudaEventRecord(e1));
+    DLAF_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    DLAF_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    const double ops = 2.0 * 128 * 256 * 32 * double(iters) * nsm;
+    best = ops / ms / 1e9 > best ? ops / ms / 1e9 : best;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;  // TOP/s (1e12 int8 multiply-adds x 2 per second)
+}

@@ -34,6 +34,9 @@ DLAF_EXTERN_C void dlaf_b200_read_profile(int ctx, double out[3]) DLAF_NOEXCEPT;
 DLAF_EXTERN_C void dlaf_b200_read_chain_profile(int ctx, double out[6]) DLAF_NOEXCEPT;
 /* fp64 tensor-pipe (DMMA.8x8x4) issue-rate peak of the current device, TFLOP/s, measured now. */
 DLAF_EXTERN_C double dlaf_b200_measure_fp64_tensor_peak_tflops(void) DLAF_NOEXCEPT;
+/* Measured int8 tensor-core peak (tcgen05.mma.kind::i8 issue rate, TOP/s): roofline denominator of the fp64
+   trailing update when it runs as exact int8 digit products (Ozaki scheme, 36 int8 MMAs per fp64 product). */
+DLAF_EXTERN_C double dlaf_b200_measure_int8_tensor_peak_tops(void) DLAF_NOEXCEPT;
 
 /* Fill this rank's HOST local part with the miniapp's random Hermitian positive definite matrix. */
 DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_s(int ctx, float* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;

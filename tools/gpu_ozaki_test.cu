@@ -131,6 +131,42 @@ int main() {
     }
   }
 
+  // ---- phase clocks of one launch (4096 x 4096 full update: 2048 tiles)
+  {
+    const int K = 512, n = 4096;
+    double *dP, *dC;
+    cudaMalloc(&dC, (size_t)n * n * 8); cudaMalloc(&dP, (size_t)n * K * 8);
+    cudaMemset(dC, 0, (size_t)n * n * 8);
+    std::vector<double> hp((size_t)n * K);
+    for (auto& x : hp) x = dist(rng);
+    cudaMemcpy(dP, hp.data(), hp.size() * 8, cudaMemcpyHostToDevice);
+    OzakiSplit sp; sp.allocate(n, K); sp.split(dP, n, n, 0);
+    GemmArgs g{};
+    g.C = dC; g.ldc = n; g.M = n; g.N = n; g.K = K; g.alpha = -1.0; g.beta = 1.0; g.mask = kMaskNone; g.nbp = 512; g.P = g.Q = 1;
+    launch_gemm_ozaki_i8(g, sp, 0, sp, 0, 0);
+    long long* dtr; cudaMalloc(&dtr, 4096 * 8 * 8); cudaMemset(dtr, 0, 4096 * 8 * 8);
+    ozaki_set_clock_trace(dtr);
+    launch_gemm_ozaki_i8(g, sp, 0, sp, 0, 0);
+    DLAF_CUDA_CHECK(cudaDeviceSynchronize());
+    ozaki_set_clock_trace(nullptr);
+    std::vector<long long> tr(4096 * 8);
+    cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost);
+    const char* names[6] = {"setup", "first_stage_wait", "mma_issue", "mma_drain", "epilogue", "teardown"};
+    for (int range = 0; range < 2; ++range) {  // first wave (cold) / later CTAs
+      double sum[6] = {0, 0, 0, 0, 0, 0}, tot = 0; int cnt = 0;
+      for (int c = range == 0 ? 0 : 148; c < (range == 0 ? 148 : 2048); ++c) {
+        const long long* t = &tr[c * 8];
+        if (t[6] == 0) continue;
+        for (int q = 0; q < 6; ++q) sum[q] += (double)(t[q + 1] - t[q]);
+        tot += (double)(t[6] - t[0]); ++cnt;
+      }
+      std::printf("ozaki phase clocks (%s, %d CTAs), avg clk:", range == 0 ? "first wave" : "later waves", cnt);
+      for (int q = 0; q < 6; ++q) std::printf(" %s %.0f", names[q], sum[q] / cnt);
+      std::printf(" | total %.0f clk = %.2f us @1.965 GHz\n", tot / cnt, tot / cnt / 1965.0);
+    }
+    sp.release(); cudaFree(dP); cudaFree(dC); cudaFree(dtr);
+  }
+
   // ---- timing
   {
     const int K = 512;

@@ -551,12 +551,15 @@ void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long
   p.scale_b = sb.scale;
   p.gx = a.M / OBM;
   p.gy = a.N / OBN;
-  // DLAF_B200_OZAKI_TPC: tiles per CTA (default 4: ~50 us CTAs)
-  static const int tpc = [] {
+  // Tiles per CTA: large launches amortise set-up over up to 8 tiles (~100 us CTAs), small ones keep every SM busy
+  // (measured in the full POTRF, profiles/r01_ozaki_tpc_sweep.log). DLAF_B200_OZAKI_TPC overrides.
+  static const int tpc_env = [] {
     const char* e = std::getenv("DLAF_B200_OZAKI_TPC");
-    const int v = e ? std::atoi(e) : 4;
-    return v < 1 ? 1 : v;
+    return e ? std::atoi(e) : 0;
   }();
+  const long grid_tiles = static_cast<long>(p.gx) * p.gy;
+  int tpc = tpc_env > 0 ? tpc_env : static_cast<int>(grid_tiles / (148 * 16));
+  tpc = tpc < 1 ? 1 : (tpc > 8 && tpc_env <= 0 ? 8 : tpc);
   p.tiles_per_cta = tpc;
   const long ntiles = static_cast<long>(p.gx) * p.gy;
   const unsigned grid = static_cast<unsigned>((ntiles + tpc - 1) / tpc);

@@ -11,7 +11,27 @@
 
 namespace dlaf_b200 {
 
+// sm_partition.cu
+cudaStream_t create_bulk_stream_with_reserved_sms(int reserve_sms, int priority);
+
 namespace {
+// DLAF_B200_RESERVE_SMS: SMs kept free of bulk-update CTAs for the panel chain (0 = off)
+// Default: 8 on grids of 4 or more GPUs, where the run is bound by the panel chain almost from the first step
+// (measured N = 32768: 2x2 grid +2.6 %, single GPU -2 %: profiles/r01_sm_reservation.log).
+int reserved_sms(int ranks) {
+  static const int v = [] {
+    const char* e = std::getenv("DLAF_B200_RESERVE_SMS");
+    return e ? std::atoi(e) : -1;
+  }();
+  return v >= 0 ? v : (ranks >= 4 ? 8 : 0);
+}
+cudaStream_t make_bulk_stream(int priority, int ranks) {
+  cudaStream_t st = create_bulk_stream_with_reserved_sms(reserved_sms(ranks), priority);
+  if (st == nullptr)
+    DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, priority));
+  return st;
+}
+
 // default fp64 bulk-update engine when DLAF_B200_D_BULK is not set
 constexpr bool kOzakiDefault = true;
 
@@ -41,7 +61,7 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
   DLAF_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
   DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sH_, cudaStreamNonBlocking, greatest));
   DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sM_, cudaStreamNonBlocking, greatest));
-  DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sL_, cudaStreamNonBlocking, least));
+  sL_ = make_bulk_stream(least, g.P * g.Q);
   DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start_, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evP_[i], cudaEventDisableTiming));
@@ -822,10 +842,8 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
     sLc_.push_back(sL_);
   while (static_cast<int>(sLc_.size()) < nc) {
     int least, greatest;
-    cudaStream_t st;
     DLAF_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, least));
-    sLc_.push_back(st);
+    sLc_.push_back(make_bulk_stream(least, geo_.P * geo_.Q));
   }
   while (static_cast<int>(evBc_.size()) < 2 * nc) {
     cudaEvent_t e;

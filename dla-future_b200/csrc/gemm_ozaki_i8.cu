@@ -10,7 +10,7 @@
 // Operands: OzakiSplit (split_i8_kernel below): 8 int8 digit planes per panel, K-major, + one power-of-two scale
 // per row. CTA = one 128 x 64 tile of C; TMEM holds the 8 anti-diagonal group accumulators (8 x 64 columns of int32
 // = all 512 columns). 6 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..9 = epilogue (TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4). Each CTA handles a few
+// warps 2..17 = epilogue (TMEM lane quadrant = warp % 4, column quarter = (warp - 2) / 4). Each CTA handles a few
 // consecutive tiles (DLAF_B200_OZAKI_TPC).
 // Pipeline: 2 stages x {8 A planes (128 rows x 64 k), 8 B planes (64 rows x 64 k)} = 96 KB per stage, loaded by two
 // 3-D TMA boxes (k, row, plane) in SWIZZLE_64B K-major UMMA layout; 24 tcgen05.mma.kind::i8 (M128, N up to 256, K32) per
@@ -39,8 +39,8 @@ constexpr int B_PLANE_BYTES = OBN * OBK;  // 4 KB
 constexpr int A_STAGE_BYTES = S * A_PLANE_BYTES;
 constexpr int B_STAGE_BYTES = S * B_PLANE_BYTES;
 constexpr int OSTAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 96 KB
-constexpr int OEPI_WARPS = 8;
-constexpr int OTHREADS = 64 + 32 * OEPI_WARPS;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int OEPI_WARPS = 16;
+constexpr int OTHREADS = 64 + 32 * OEPI_WARPS;  // TMA warp, MMA warp, 16 epilogue warps
 constexpr int OSMEM_BYTES = OSTAGES * OSTAGE_BYTES + 1024 /*alignment slack*/ + 2048 /*barriers + column scales*/;
 constexpr int kRowChunk = 64;  // row tiles per rasterization chunk
 constexpr uint32_t kTmemCols = 512;  // group g at columns [64 g, 64 g + 64)
@@ -106,13 +106,6 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-
 // Measurement aid: when non-null, CTAs with linear index < kDbgCtas record clock64() at 7 phase boundaries.
 __device__ long long* g_ozaki_clock_trace = nullptr;
 constexpr int kDbgCtas = 4096;
@@ -140,6 +133,41 @@ struct OzakiParams {
 // signed 64-bit integer (|v| < 2^51) -> double, exactly, on the integer + fp64-add pipes (no I2F)
 __device__ __forceinline__ double i64_to_f64_exact(long long v) {
   return __longlong_as_double(0x4330000000000000LL + (v + (1LL << 51))) - 0x1.8p52;
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+
+// Fold + store of one thread's row segment (HC columns) of a finished tile. FULL = the tile lies entirely in the
+// lower triangle (no element mask, branch-free); otherwise `lim` = number of leading columns of the segment that are
+// on or below the diagonal for this row.
+template <bool FULL, int HC>
+__device__ __forceinline__ void ozaki_fold_store(uint32_t taddr, double* Cg, long ldc, const double (&cv)[HC],
+                                                 double row_scale, const double* cs, int lim) {
+#pragma unroll
+  for (int c0 = 0; c0 < HC; c0 += 4) {
+    int acc[S][4];
+#pragma unroll
+    for (int g = 0; g < S; ++g)
+      tmem_ld4(taddr + static_cast<uint32_t>(g * OBN + c0), acc[g]);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // sum_g acc_g 128^-g = (hi + lo 2^-28) 2^-21 with two exact 46-bit integers
+      const long long hi = (static_cast<long long>(acc[0][j]) << 21) + (static_cast<long long>(acc[1][j]) << 14) +
+                           (static_cast<long long>(acc[2][j] * 128 + acc[3][j]));
+      const long long lo = (static_cast<long long>(acc[4][j]) << 21) + (static_cast<long long>(acc[5][j]) << 14) +
+                           (static_cast<long long>(acc[6][j] * 128 + acc[7][j]));
+      const double v = fma(i64_to_f64_exact(lo), 0x1p-28, i64_to_f64_exact(hi));
+      const double o = fma(v, row_scale * cs[c0 + j], cv[c0 + j]);
+      if (FULL || c0 + j < lim)
+        Cg[static_cast<long>(c0 + j) * ldc] = o;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(OTHREADS, 1)
@@ -282,11 +310,12 @@ __global__ void __launch_bounds__(OTHREADS, 1)
     }
   }
   else {
-    // ===== epilogue: 8 warps; TMEM lane quadrant = warp % 4, column half = (warp - 2) / 4 =====
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // ===== epilogue: 16 warps; TMEM lane quadrant = warp % 4, column quarter = (warp - 2) / 4 =====
+    const int q = warp & 3, part = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row of the tile held by this thread
-    const int e = threadIdx.x - 64;  // 0..255
-    constexpr int HC = OBN / 2;      // columns per thread
+    const int e = threadIdx.x - 64;  // 0 .. 32 * OEPI_WARPS - 1
+    constexpr int HC = OBN / (OEPI_WARPS / 4);  // columns per thread
+    const int cb = part * HC;
     int tcount = 0;
     for (int l = first; l < last; ++l) {
       int row0, col0;
@@ -298,43 +327,27 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       if (e < OBN)
         cs[e] = p.scale_b[p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp + e];
       const double row_scale = p.scale_a[p.a_row + row0 + r] * p.alpha * 0x1p-35;  // 2^-14 digits, 2^-21 from the fold
-      const int cb = half * HC;
       double* Cg = p.C + row0 + r + static_cast<long>(col0 + cb) * p.ldc;
-      const long gr = grow0 + r, gc = gcol0 + cb;
+      // columns [0, lim) of this thread's segment are on or below the diagonal
+      const long room = (grow0 + r) - (gcol0 + cb) + 1;
+      const int lim = (cls == 1) ? HC : (room < 0 ? 0 : (room > HC ? HC : static_cast<int>(room)));
       // The C row segment of this thread is fetched while the MMAs run: after the accumulators complete only TMEM
       // loads, the integer fold, two exact conversions and the stores remain.
       double cv[HC];
 #pragma unroll
-      for (int j = 0; j < HC; ++j) {
-        const bool on = (cls == 1) || (gr >= gc + j);
-        cv[j] = on ? Cg[static_cast<long>(j) * p.ldc] : 0.0;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // column scales of this tile are in place
+      for (int j = 0; j < HC; ++j)
+        cv[j] = (j < lim) ? Cg[static_cast<long>(j) * p.ldc] : 0.0;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * OEPI_WARPS) : "memory");  // column scales of this tile are in place
       mbar_wait(tmem_full, tcount & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (threadIdx.x == 64 && tcount == 0)
         OZ_TRACE(4);
-#pragma unroll
-      for (int c0 = 0; c0 < HC; c0 += 8) {
-        int acc[S][8];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb + c0);
-#pragma unroll
-        for (int g = 0; g < S; ++g)
-          tmem_ld8(taddr + static_cast<uint32_t>(g * OBN), acc[g]);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (cls != 1 && (gr < gc + c0 + j))
-            continue;
-          // sum_g acc_g 128^-g = (hi + lo 2^-28) 2^-21 with two exact 46-bit integers
-          const long long hi = (static_cast<long long>(acc[0][j]) << 21) + (static_cast<long long>(acc[1][j]) << 14) +
-                               (static_cast<long long>(acc[2][j]) << 7) + acc[3][j];
-          const long long lo = (static_cast<long long>(acc[4][j]) << 21) + (static_cast<long long>(acc[5][j]) << 14) +
-                               (static_cast<long long>(acc[6][j]) << 7) + acc[7][j];
-          const double v = fma(i64_to_f64_exact(lo), 0x1p-28, i64_to_f64_exact(hi));
-          Cg[static_cast<long>(c0 + j) * p.ldc] = fma(v, row_scale * cs[cb + c0 + j], cv[c0 + j]);
-        }
-      }
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb);
+      // tcgen05.ld is warp-collective (.sync.aligned): the path must be chosen per WARP, never per thread
+      if (__all_sync(0xffffffffu, lim == HC))
+        ozaki_fold_store<true, HC>(taddr, Cg, p.ldc, cv, row_scale, cs + cb, lim);
+      else
+        ozaki_fold_store<false, HC>(taddr, Cg, p.ldc, cv, row_scale, cs + cb, lim);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0)
@@ -558,8 +571,9 @@ void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long
     return e ? std::atoi(e) : 0;
   }();
   const long grid_tiles = static_cast<long>(p.gx) * p.gy;
-  int tpc = tpc_env > 0 ? tpc_env : static_cast<int>(grid_tiles / (148 * 16));
-  tpc = tpc < 1 ? 1 : (tpc > 8 && tpc_env <= 0 ? 8 : tpc);
+  int tpc = tpc_env;
+  if (tpc <= 0)  // trailing matrix >= 16K: 8, >= 8K: 4, >= 4K: 2
+    tpc = grid_tiles >= 32768 ? 8 : (grid_tiles >= 8192 ? 4 : (grid_tiles >= 2048 ? 2 : 1));
   p.tiles_per_cta = tpc;
   const long ntiles = static_cast<long>(p.gx) * p.gy;
   const unsigned grid = static_cast<unsigned>((ntiles + tpc - 1) / tpc);

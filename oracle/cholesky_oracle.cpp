@@ -420,6 +420,30 @@ double residual(char uplo, long n, const T* a, long lda, const T* f, long ldf) {
     return residual<T>(uplo, n, static_cast<const T*>(a), lda, static_cast<const T*>(f), ldf);   \
   }
 
+// The four tile operations exactly as cholesky_local() calls them (wrappers above), exported so that the tests can
+// pin their argument conventions against the reference's own tile known-answer tests
+// (test/unit/test_blas_tile/test_{gemm,herk,trsm}.h, test/unit/test_lapack_tile/test_potrf.h).
+#define EXPORT_TILE_OPS(sfx, T)                                                                                     \
+  extern "C" void oracle_tile_trsm_##sfx(char side, char uplo, char op, char diag, int m, int n, const void* alpha, \
+                                         const void* a, int lda, void* b, int ldb) {                                \
+    trsm(side, uplo, op, diag, m, n, *static_cast<const T*>(alpha), static_cast<const T*>(a), lda,                  \
+         static_cast<T*>(b), ldb);                                                                                  \
+  }                                                                                                                 \
+  extern "C" void oracle_tile_gemm_##sfx(char opa, char opb, int m, int n, int k, const void* alpha, const void* a, \
+                                         int lda, const void* b, int ldb, const void* beta, void* c, int ldc) {     \
+    gemm(opa, opb, m, n, k, *static_cast<const T*>(alpha), static_cast<const T*>(a), lda,                           \
+         static_cast<const T*>(b), ldb, *static_cast<const T*>(beta), static_cast<T*>(c), ldc);                     \
+  }                                                                                                                 \
+  extern "C" void oracle_tile_herk_##sfx(char uplo, char op, int n, int k, double alpha, const void* a, int lda,    \
+                                         double beta, void* c, int ldc) {                                           \
+    herk(uplo, op, n, k, static_cast<BaseT<T>>(alpha), static_cast<const T*>(a), lda, static_cast<BaseT<T>>(beta),  \
+         static_cast<T*>(c), ldc);                                                                                  \
+  }
+EXPORT_TILE_OPS(s, float)
+EXPORT_TILE_OPS(d, double)
+EXPORT_TILE_OPS(c, std::complex<float>)
+EXPORT_TILE_OPS(z, std::complex<double>)
+
 EXPORT_TYPE(s, float)
 EXPORT_TYPE(d, double)
 EXPORT_TYPE(c, std::complex<float>)

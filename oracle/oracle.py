@@ -45,6 +45,19 @@ def lib() -> ctypes.CDLL:
             f = getattr(_LIB, f"oracle_set_random_hpd_{t}")
             f.argtypes = [ctypes.c_long, ctypes.c_long, ctypes.c_void_p, ctypes.c_long]
             f.restype = None
+            f = getattr(_LIB, f"oracle_tile_trsm_{t}")
+            f.argtypes = [ctypes.c_char] * 4 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                ctypes.c_void_p, ctypes.c_int]
+            f.restype = None
+            f = getattr(_LIB, f"oracle_tile_gemm_{t}")
+            f.argtypes = [ctypes.c_char] * 2 + [ctypes.c_int] * 3 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                                       ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                                       ctypes.c_void_p, ctypes.c_int]
+            f.restype = None
+            f = getattr(_LIB, f"oracle_tile_herk_{t}")
+            f.argtypes = [ctypes.c_char] * 2 + [ctypes.c_int] * 2 + [ctypes.c_double, ctypes.c_void_p, ctypes.c_int,
+                                                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_int]
+            f.restype = None
             f = getattr(_LIB, f"oracle_residual_{t}")
             f.argtypes = [ctypes.c_char, ctypes.c_long, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
                           ctypes.c_long]
@@ -69,7 +82,11 @@ def type_char(dtype) -> str:
 
 
 def _check_fortran(a: np.ndarray):
-    assert a.ndim == 2 and a.flags.f_contiguous, "column-major (Fortran-order) array expected"
+    """Column-major storage: unit stride down the columns, any leading dimension >= rows (sub-views of a Fortran
+    array included, like a tile inside a slab)."""
+    assert a.ndim == 2, "2-D array expected"
+    ok = a.flags.f_contiguous or a.size == 0 or (a.strides[0] == a.itemsize and (a.shape[1] <= 1 or a.strides[1] >= a.shape[0] * a.itemsize))
+    assert ok, "column-major (Fortran-order) array expected"
 
 
 def cholesky_local(uplo: str, a: np.ndarray, nb: int, nthreads: int = 1) -> int:
@@ -80,6 +97,36 @@ def cholesky_local(uplo: str, a: np.ndarray, nb: int, nthreads: int = 1) -> int:
     lda = max(1, a.strides[1] // a.itemsize) if n > 0 else 1
     f = getattr(lib(), f"oracle_cholesky_local_{type_char(a.dtype)}")
     return f(uplo.encode(), n, nb, a.ctypes.data, lda, nthreads)
+
+
+def _scalar(dtype, v):
+    return np.array([v], dtype=dtype)
+
+
+def tile_trsm(side: str, uplo: str, op: str, diag: str, m: int, n: int, alpha, a: np.ndarray, lda: int, b: np.ndarray,
+              ldb: int) -> None:
+    """The oracle's tile TRSM wrapper (what trsmPanelTile calls, impl.h:55-67 / :107-119), B (m x n) in place."""
+    t = type_char(b.dtype)
+    al = _scalar(b.dtype, alpha)
+    getattr(lib(), f"oracle_tile_trsm_{t}")(side.encode(), uplo.encode(), op.encode(), diag.encode(), m, n,
+                                             al.ctypes.data, a.ctypes.data, lda, b.ctypes.data, ldb)
+
+
+def tile_gemm(opa: str, opb: str, m: int, n: int, k: int, alpha, a: np.ndarray, lda: int, b: np.ndarray, ldb: int, beta,
+              c: np.ndarray, ldc: int) -> None:
+    """The oracle's tile GEMM wrapper (gemmTrailingMatrixTile, impl.h:82-94 / :134-146), C in place."""
+    t = type_char(c.dtype)
+    al, be = _scalar(c.dtype, alpha), _scalar(c.dtype, beta)
+    getattr(lib(), f"oracle_tile_gemm_{t}")(opa.encode(), opb.encode(), m, n, k, al.ctypes.data, a.ctypes.data, lda,
+                                             b.ctypes.data, ldb, be.ctypes.data, c.ctypes.data, ldc)
+
+
+def tile_herk(uplo: str, op: str, n: int, k: int, alpha: float, a: np.ndarray, lda: int, beta: float, c: np.ndarray,
+              ldc: int) -> None:
+    """The oracle's tile HERK/SYRK wrapper (herkTrailingDiagTile, impl.h:69-80 / :121-132), C in place."""
+    t = type_char(c.dtype)
+    getattr(lib(), f"oracle_tile_herk_{t}")(uplo.encode(), op.encode(), n, k, float(alpha), a.ctypes.data, lda,
+                                             float(beta), c.ctypes.data, ldc)
 
 
 def lapack_potrf(uplo: str, a: np.ndarray, nthreads: int) -> int:

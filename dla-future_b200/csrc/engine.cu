@@ -62,12 +62,15 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
   DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sH_, cudaStreamNonBlocking, greatest));
   DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sM_, cudaStreamNonBlocking, greatest));
   sL_ = make_bulk_stream(least, g.P * g.Q);
+  DLAF_CUDA_CHECK(cudaStreamCreateWithPriority(&sR_, cudaStreamNonBlocking, greatest));
   DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start_, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evP_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evB_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evC_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evD_[i], cudaEventDisableTiming));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evF_[i], cudaEventDisableTiming));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evT1_[i], cudaEventDisableTiming));
   }
   const size_t wsz = static_cast<size_t>(ns_) * G * G;
   const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
@@ -90,6 +93,8 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
     const char* e = std::getenv("DLAF_B200_D_BULK");
     const bool want = (e != nullptr) ? (std::string(e) == "ozaki") : kOzakiDefault;
     use_ozaki_ = want && nt_ > 1 && ltr_ > 0 && ltc_ > 0 && nbp_ <= 512;
+    const char* sc = std::getenv("DLAF_B200_SPLIT_CHAIN");
+    split_chain_ = use_ozaki_ && geo_.P * geo_.Q == 1 && (sc == nullptr || std::atoi(sc) != 0);
     if (use_ozaki_)
       for (int i = 0; i < 2; ++i) {
         osplit_[i].allocate(static_cast<long>(ltr_) * nbp_, nbp_);
@@ -114,7 +119,11 @@ PotrfEngine<T>::~PotrfEngine() {
   cudaStreamSynchronize(sH_);
   cudaStreamSynchronize(sM_);
   cudaStreamSynchronize(sL_);
+  cudaStreamSynchronize(sR_);
+  cudaStreamDestroy(sR_);
   for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(evF_[i]);
+    cudaEventDestroy(evT1_[i]);
     cudaEventDestroy(evC_[i]);
     cudaEventDestroy(evD_[i]);
     cudaFree(wbuf_[i]);
@@ -430,6 +439,38 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       chain_stamp(k, 2);
       chain_stamp(k, 3);
     }
+    if (mt > 0 && split_chain()) {
+      // Two chains instead of one (1 x 1 grid, int8 engine): the critical stream only solves the FIRST tile row of
+      // the panel — all the next diagonal tile needs (its update then runs on native fp64, straight from that
+      // tile) — while stream R solves the rest, cuts the digit planes and publishes the panel (evP) to the
+      // column / bulk updates:      H: potrf(k) | trsm(k+1,k) | update(k+1,k+1) | potrf(k+1) ...
+      //                             R:          | trsm(rows k+2..) | split | evP(k)
+      DLAF_CUDA_CHECK(cudaEventRecord(evF_[slot], sH_));
+      if (wait_column)  // rows of block column k below the diagonal tile: updated on stream M
+        DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evC_[(k - 1) % 2], 0));
+      trsm_panel(tile_ptr(li1, lkc), ld_, nbp_, tkk, ldt, w, sH_);
+      DLAF_CUDA_CHECK(cudaEventRecord(evT1_[slot], sH_));
+      wait_columns(lkc + 1, sR_);
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evF_[slot], 0));
+      if (wait_column)
+        DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evC_[(k - 1) % 2], 0));
+      if (mt > 1)
+        trsm_panel(tile_ptr(li1 + 1, lkc), ld_, (mt - 1) * nbp_, tkk, ldt, w, sR_);
+      if (k < nt_ - 1) {
+        if (k >= 2)  // the digit planes of this slot were last read by the updates of step k-2
+          wait_bulk(k - 2, -1, sR_);
+        DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evT1_[slot], 0));
+        if constexpr (std::is_same_v<T, double>) {
+          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sR_);
+          ++launches_;
+        }
+      }
+      chain_stamp(k, 4);
+      chain_stamp(k, 5);
+      DLAF_CUDA_CHECK(cudaEventRecord(evP_[slot], sR_));
+      download_column(lkc, evP_[slot]);
+      return;
+    }
     if (mt > 0) {
       if (wait_column)  // rows of block column k below the diagonal tile: updated on stream M
         DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evC_[(k - 1) % 2], 0));
@@ -513,7 +554,8 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
 // U_k on my local block columns [cj0, cj0 + ncols), rows from local tile row ri0 on (mrows elements):
 // ONE masked GEMM launch.
 template <class T>
-void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows, bool count_flops, cudaStream_t st) {
+void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows, bool count_flops, cudaStream_t st,
+                                   bool native) {
   const int P = geo_.P, Q = geo_.Q;
   const int li1 = cnt_rows(k + 1), lj1 = cnt_cols(k + 1);
   const long gj0 = static_cast<long>(cj0) * Q + geo_.pcol;
@@ -593,7 +635,7 @@ void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows
     }
   }
   if constexpr (std::is_same_v<T, double>) {
-    if (use_ozaki_) {
+    if (use_ozaki_ && !native) {
       const long a_row = static_cast<long>(ri0 - li1) * nbp_;
       if (P > 1)
         launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplitT_[slot], static_cast<long>(cj0 - lj1) * nbp_, st);
@@ -651,7 +693,7 @@ void PotrfEngine<T>::update(int k, UpdatePart part, cudaStream_t st) {
     return;
   const int cend = cj0 + ncols;
   wait_columns(cend, st);
-  launch_update(k, cj0, ncols, ri0, mrows, part == kBulk, st);
+  launch_update(k, cj0, ncols, ri0, mrows, part == kBulk, st, part == kNextDiag && split_chain());
 }
 
 // ---- host pipelining (factorize_host) -------------------------------------------------------------
@@ -820,6 +862,7 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   DLAF_CUDA_CHECK(cudaMemsetAsync(d_info_, 0, sizeof(int), sH_));
 
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, ev_start_, 0));
+  DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, ev_start_, 0));
   if (host_) {
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sIn_, ev_start_, 0));
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sOut_, ev_start_, 0));

@@ -104,7 +104,8 @@ private:
   void panel_step(int k, bool wait_column);
   enum UpdatePart { kBulk = 0, kNextDiag = 1, kNextColumnRest = 2 };
   void update(int k, UpdatePart part, cudaStream_t st);
-  void launch_update(int k, int cj0, int ncols, int ri0, int mrows, bool count_flops, cudaStream_t st);
+  void launch_update(int k, int cj0, int ncols, int ri0, int mrows, bool count_flops, cudaStream_t st,
+                     bool native = false);
   void factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_t st);
   void trsm_panel(T* b, long ldb, int m, const T* tkk, long ldt, const T* w, cudaStream_t st);
   void gemm(const GemmArgsT<T>& a, cudaStream_t st);
@@ -158,6 +159,12 @@ private:
   OzakiSplit osplit_[2];
   OzakiSplit osplitT_[2];
   bool split_panels() const { return use_tf32_ || use_ozaki_; }
+  // 1 x 1 grid, int8 engine: the panel of a step is finished on stream R while stream H already goes on with the next
+  // diagonal tile (engine.cu: panel_step). DLAF_B200_SPLIT_CHAIN=0 keeps everything on stream H.
+  bool split_chain_ = false;
+  bool split_chain() const { return split_chain_; }
+  cudaStream_t sR_ = nullptr;
+  cudaEvent_t evF_[2] = {nullptr, nullptr}, evT1_[2] = {nullptr, nullptr};
   int* d_info_ = nullptr;
   int* h_info_ = nullptr;
   long launches_ = 0;

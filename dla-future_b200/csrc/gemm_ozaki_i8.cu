@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict_
 #pragma unroll
   for (int i = 0; i < PER; ++i) {
     v[i] = live ? x[roff + static_cast<long>(kg * PER + i) * ld] : 0.0;
-    m = fmax(m, fabs(v[i]));
+    m = isfinite(v[i]) ? fmax(m, fabs(v[i])) : INFINITY;  // Inf / NaN poison the whole row (see the scale below)
   }
   smax[kg][tr] = m;
   __syncthreads();
@@ -397,8 +397,10 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict_
     e = ilogb(m) + 2;
   e = e < -1000 ? -1000 : (e > 1000 ? 1000 : e);
   const double down = __hiloint2double((1023 - e) << 20, 0);  // 2^-e
+  // A row holding Inf / NaN gets a NaN scale: every C entry it contributes to becomes NaN, like in a native fp64 update
+  // (the digits themselves cannot carry non-finite values).
   if (kg == 0 && live)
-    scale[r] = __hiloint2double((1023 + e) << 20, 0);  // 2^e
+    scale[r] = (m < INFINITY) ? __hiloint2double((1023 + e) << 20, 0) : __longlong_as_double(0x7FF8000000000000LL);
 #pragma unroll
   for (int i = 0; i < PER; ++i)
     v[i] *= down;

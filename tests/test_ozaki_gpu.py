@@ -71,3 +71,27 @@ def test_ozaki_wide_dynamic_range(pkg, oracle):
     tol = oracle.cholesky_tolerance(n, np.float64)
     ok, _, msg = oracle.check_near(np.tril(ref) / d[:, None], np.tril(out) / d[:, None], tol, tol)
     assert ok, msg
+
+
+@pytest.mark.parametrize("engine", ["ozaki", "dmma"])
+def test_nan_in_the_input_is_not_swallowed(pkg, oracle, engine):
+    """A NaN below the diagonal must surface (non-zero info, like a non-SPD input), never be rounded to a digit."""
+    n, nb = 1024, 256
+    a = oracle.set_random_hermitian_positive_definite(n, nb, np.float64)
+    a[n - 3, 5] = np.nan
+    old = os.environ.get("DLAF_B200_D_BULK")
+    os.environ["DLAF_B200_D_BULK"] = engine
+    try:
+        pkg.initialize()
+        ctx = pkg.create_grid(None, 1, 1, "R")
+        try:
+            out = a.copy(order="F")
+            info = pkg.cholesky_factorization(ctx, "L", out, nb)
+        finally:
+            pkg.free_grid(ctx)
+    finally:
+        if old is None:
+            del os.environ["DLAF_B200_D_BULK"]
+        else:
+            os.environ["DLAF_B200_D_BULK"] = old
+    assert info != 0 or np.isnan(np.tril(out)).any()

@@ -8,15 +8,19 @@
 // at the int8 tensor rate.
 //
 // Operands: OzakiSplit (split_i8_kernel below): 8 int8 digit planes per panel, K-major, + one power-of-two scale
-// per row. CTA = one 128 x 64 tile of C; TMEM holds the 8 anti-diagonal group accumulators (8 x 64 columns of int32
-// = all 512 columns). 6 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..17 = epilogue (TMEM lane quadrant = warp % 4, column quarter = (warp - 2) / 4). Each CTA handles a few
-// consecutive tiles (DLAF_B200_OZAKI_TPC).
+// per row. CTA = 128 x 64 tiles of C, a few consecutive ones per CTA (DLAF_B200_OZAKI_TPC); TMEM holds the 8
+// anti-diagonal group accumulators (8 x 64 columns of int32 = all 512 columns). 18 warps: warp 0 = TMA producer
+// (one lane), warp 1 = TMEM allocator + MMA issuer (one lane), warps 2..17 = epilogue (TMEM lane quadrant = warp % 4,
+// column quarter = (warp - 2) / 4).
 // Pipeline: 2 stages x {8 A planes (128 rows x 64 k), 8 B planes (64 rows x 64 k)} = 96 KB per stage, loaded by two
-// 3-D TMA boxes (k, row, plane) in SWIZZLE_64B K-major UMMA layout; 24 tcgen05.mma.kind::i8 (M128, N up to 256, K32) per
-// stage (one instruction covers up to 4 digit-plane pairs, see the issuer loop); full/empty mbarriers, tcgen05.commit releases a stage / signals the epilogue. Every wait is bounded.
-// Epilogue: per row (= TMEM lane) and 8 columns at a time, the 8 int32 group sums are folded in fp64 by Horner
-// (smallest group first), scaled by 2^(e_row + e_col - 14) and added to C with coalesced column accesses.
+// 3-D TMA boxes (k, row, plane) in SWIZZLE_64B K-major UMMA layout; 24 tcgen05.mma.kind::i8 (M128, N up to 256, K32)
+// per stage — one instruction covers up to 4 digit-plane pairs, see the issuer loop; full/empty mbarriers,
+// tcgen05.commit releases a stage / signals the epilogue, the epilogue hands TMEM back through tmem_empty. Every
+// mbarrier wait is bounded (trap instead of hang).
+// Epilogue: per row (= TMEM lane) and 4 columns at a time the 8 int32 group sums are folded EXACTLY into two 46-bit
+// integers, converted to fp64 without I2F, combined, scaled by 2^(e_row + e_col - 35) and added to the C values that
+// were fetched while the MMAs ran; coalesced column accesses; the masked variant is chosen per warp (tcgen05.ld is
+// warp-collective).
 #include <cuda.h>
 #include <cuda_runtime.h>
 

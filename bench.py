@@ -286,6 +286,44 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             log(f"[bench] residual check skipped: {e}")
 
+    # ---- precision evidence in the same run (checker): the timed result of the int8-digit engine next to the native
+    # fp64 (DMMA) engine on the same input — residuals of both and the largest difference between the two factors.
+    accuracy = None
+    if not args.no_check and world == 1 and os.environ.get("DLAF_B200_D_BULK", "ozaki") == "ozaki":
+        prev = os.environ.get("DLAF_B200_D_BULK")
+        ctx2 = None
+        try:
+            os.environ["DLAF_B200_D_BULK"] = "dmma"
+            ctx2 = pkg.create_grid(None, 1, 1, "C")  # fresh context -> fresh engine that reads the switch
+            d_nat = d_ref.clone()
+            pkg.cholesky_factorization_device(ctx2, "L", d_nat.data_ptr(), dtype, n, nb, ld, stream.cuda_stream)
+            assert pkg.wait(ctx2, stream.cuda_stream) == 0
+            res_nat = residual_check_torch(torch, d_ref.view(n, n), d_nat.view(n, n), n)
+            max_diff = max_l = 0.0
+            for j0 in range(0, n, 4096):  # [col, row] views: the lower triangle of L is the upper triangle of the view
+                j1 = min(n, j0 + 4096)
+                a_, b_ = torch.triu(d_work.view(n, n)[j0:j1, j0:]), torch.triu(d_nat.view(n, n)[j0:j1, j0:])
+                max_diff = max(max_diff, (a_ - b_).abs().max().item())
+                max_l = max(max_l, b_.abs().max().item())
+                del a_, b_
+            accuracy = {"residual_int8_digit_engine": residual, "residual_native_fp64_engine": res_nat,
+                        "max_abs_diff_between_the_two_factors": max_diff, "max_abs_factor_entry": max_l,
+                        "diff_in_ulps_of_max_entry": max_diff / (max_l * float(np.finfo(np.float64).eps)),
+                        "gate_eps_n": float(np.finfo(np.float64).eps * n)}
+            del d_nat
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] native-engine comparison skipped: {e!r}")
+        finally:
+            if ctx2 is not None:
+                try:
+                    pkg.free_grid(ctx2)
+                except Exception:
+                    pass
+            if prev is None:
+                os.environ.pop("DLAF_B200_D_BULK", None)
+            else:
+                os.environ["DLAF_B200_D_BULK"] = prev
+
     # ---- roofline of the dominant kernel (bulk trailing update on stream L)
     # fp64 engine (DLAF_B200_D_BULK): "ozaki" (default) = exact int8 digit products on tcgen05, 36 int8 MACs per fp64 MAC,
     # bounded by the int8 tensor pipe; "dmma" = native fp64 DMMA, bounded by the fp64 tensor pipe.
@@ -408,6 +446,7 @@ def run_ours(args):
                        "wall_s_incl_restore": wall},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "gpu_library_reference": gpu_ref,
+            "accuracy_vs_native_fp64_engine": accuracy,
             "residual_max_diff_over_max_a": residual,
             "residual_gate_eps_n": float(np.finfo(np.float64).eps * n),
             "step_ms": step_ms,

@@ -18,6 +18,7 @@
 
 #include "common.h"
 #include "potrf_block.cuh"
+#include "potrf_cluster.cuh"
 #include "types.h"
 
 namespace dlaf_b200 {
@@ -240,6 +241,79 @@ __global__ void __launch_bounds__(kPotrfThreads, 1)
   pblock::store_block<C, T>(reg, Tm, ldt, W, ldw, dd, dinv, ti, tj);
 }
 
+// ---- the two-CTA cluster variant (potrf_cluster.cuh) --------------------------------------------
+template <class T>
+struct DevClusterCtx {
+  using R = base_t<T>;
+  int cta, tid;
+  T* panel[2];
+  R *dd, *dinv, *dfinv, *dfsq;
+  T *dfL, *msc;
+  int* sfail;
+  unsigned peer;
+  __host__ __device__ void cta_sync() {
+#ifdef __CUDA_ARCH__
+    __syncthreads();
+#endif
+  }
+  // release / acquire at cluster scope: the DSMEM stores issued before the barrier are visible to the peer after it
+  __host__ __device__ void cluster_sync() {
+#ifdef __CUDA_ARCH__
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+#endif
+  }
+  template <class V>
+  __host__ __device__ void push(V* local, V v) {
+#ifdef __CUDA_ARCH__
+    static_assert(sizeof(V) == 4 || sizeof(V) == 8 || sizeof(V) == 16, "push: 4, 8 or 16 byte values");
+    const unsigned la = static_cast<unsigned>(__cvta_generic_to_shared(local));
+    unsigned ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(peer));
+    if constexpr (sizeof(V) == 4) {
+      asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(*reinterpret_cast<const unsigned*>(&v)) : "memory");
+    }
+    else if constexpr (sizeof(V) == 8) {
+      asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(ra), "l"(*reinterpret_cast<const unsigned long long*>(&v)) : "memory");
+    }
+    else {
+      const unsigned long long* q = reinterpret_cast<const unsigned long long*>(&v);
+      asm volatile("st.shared::cluster.v2.u64 [%0], {%1, %2};" ::"r"(ra), "l"(q[0]), "l"(q[1]) : "memory");
+    }
+#else
+    (void) local;
+    (void) v;
+#endif
+  }
+};
+
+template <class T, int PB>
+__global__ void __cluster_dims__(pblock::kClusterCtas, 1, 1) __launch_bounds__(pblock::kClusterThreads, 1)
+    potrf_inv_cluster2_kernel(T* __restrict__ Tm, long ldt, T* __restrict__ W, long ldw, int* info, int info_offset) {
+  using C = pblock::Cfg<T, PB>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevClusterCtx<T> cx;
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  cx.cta = static_cast<int>(rank);
+  cx.peer = rank ^ 1u;
+  cx.tid = threadIdx.x;
+  pblock::ClusterSmem<C, T>::carve(cx, smem_raw);
+  pblock::potrf_inv_cluster2_body<C, T>(cx, Tm, ldt, W, ldw, info, info_offset);
+  // no CTA of the pair may exit while the other one can still store into its shared memory: every push is followed
+  // by a cluster barrier inside the body, and the last statement of the body touches only global memory
+}
+
+template <class T>
+void launch_cluster2(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
+  constexpr int PB = Gran<T>::value;
+  using C = pblock::Cfg<T, PB>;
+  constexpr int smem = static_cast<int>(pblock::ClusterSmem<C, T>::bytes);
+  static_assert(smem <= 48 * 1024, "cluster kernel shared memory");
+  potrf_inv_cluster2_kernel<T, PB><<<pblock::kClusterCtas, pblock::kClusterThreads, smem, stream>>>(t, ldt, w, ldw, info,
+                                                                                                   info_offset);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+
 template <class T>
 void launch_blocked(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
   constexpr int PB = Gran<T>::value;
@@ -251,11 +325,17 @@ void launch_blocked(T* t, long ldt, T* w, long ldw, int* info, int info_offset, 
 
 template <class T>
 void launch_impl(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
-  // DLAF_B200_POTRF_KERNEL=sweep selects the simple shared-memory sweep (kept for A/B measurements)
-  static const bool use_sweep = [] {
+  // DLAF_B200_POTRF_KERNEL=sweep selects the simple shared-memory sweep (kept for A/B measurements),
+  // =cluster2 the two-SM cluster variant (potrf_cluster.cuh; validated by host emulation, not yet timed on a GPU)
+  static const std::string variant = [] {
     const char* e = std::getenv("DLAF_B200_POTRF_KERNEL");
-    return e && std::string(e) == "sweep";
+    return std::string(e ? e : "");
   }();
+  static const bool use_sweep = (variant == "sweep");
+  if (variant == "cluster2") {
+    launch_cluster2<T>(t, ldt, w, ldw, info, info_offset, stream);
+    return;
+  }
   if (!use_sweep) {
     launch_blocked<T>(t, ldt, w, ldw, info, info_offset, stream);
     return;

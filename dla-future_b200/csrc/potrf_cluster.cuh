@@ -16,8 +16,9 @@
 // pointers, cta_sync, cluster_sync, push-to-peer): potrf_tile.cu instantiates it with PTX (mapa, st.shared::cluster,
 // barrier.cluster), tools/potrf_cluster_emu.cu with 256 host threads and std::barrier — the SAME code, checked on the
 // CPU against host loops (there is no GPU in the build container).
-// Status: selected with DLAF_B200_POTRF_KERNEL=cluster2; the default stays the single-CTA kernel until this one has
-// been timed on a B200.
+// Status: selected with DLAF_B200_POTRF_KERNEL=cluster2. One GPU run so far (tools/potrf_variant_probe.py): correct at
+// once, 326 vs 342 us per 512-tile — less than the model above predicts, so the default stays the single-CTA kernel
+// until the per-phase clocks of this one have been looked at.
 #pragma once
 
 #include "potrf_block.cuh"

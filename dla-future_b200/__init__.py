@@ -32,7 +32,8 @@ C_API_SYMBOLS = [
     *[f"dlaf_p{t}potrf" for t in "sdcz"],
     *[f"dlaf_b200_cholesky_factorization_device_{t}" for t in "sdcz"],
     *[f"dlaf_b200_set_random_hermitian_positive_definite_{t}" for t in "sdcz"],
-    *[f"dlaf_b200_check_cholesky_{t}" for t in "sdcz"], "dlaf_b200_grid_barrier",
+    *[f"dlaf_b200_check_cholesky_{t}" for t in "sdcz"], *[f"dlaf_b200_check_cholesky_device_{t}" for t in "sdcz"],
+    "dlaf_b200_grid_barrier",
     "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info",
     "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops", "dlaf_b200_measure_int8_tensor_peak_tops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
@@ -130,6 +131,9 @@ def lib() -> ctypes.CDLL:
         f.restype = None
         f = getattr(L, f"dlaf_b200_check_cholesky_{t}")
         f.argtypes = [ci, cc, vp, vp, DLAF_descriptor]
+        f.restype = ctypes.c_double
+        f = getattr(L, f"dlaf_b200_check_cholesky_device_{t}")
+        f.argtypes = [ci, cc, vp, vp, DLAF_descriptor, vp]
         f.restype = ctypes.c_double
     L.dlaf_b200_grid_barrier.argtypes = [ci]
     L.dlaf_b200_grid_barrier.restype = None
@@ -304,13 +308,23 @@ def set_random_hermitian_positive_definite(ctx: int, a: np.ndarray, n: int, nb: 
     f(ctx, a.ctypes.data, d)
 
 
-def check_cholesky(ctx: int, uplo: str, a_orig: np.ndarray, factor: np.ndarray, nb: int) -> float:
-    """The miniapp's check (max|A - L L^H| / max|A| on the `uplo` triangle) evaluated on the GPU."""
-    n = a_orig.shape[0]
+def check_cholesky(ctx: int, uplo: str, a_orig: np.ndarray, factor: np.ndarray, nb: int, n: int | None = None,
+                   isrc: int = 0, jsrc: int = 0) -> float:
+    """The miniapp's check (max|A - L L^H| / max|A| on the `uplo` triangle of the GLOBAL matrix) evaluated on the GPUs of
+    the grid; collective: every rank passes its HOST local parts (input, result) and gets the same value."""
+    n = a_orig.shape[0] if n is None else n
     assert _ld_of(a_orig) == _ld_of(factor)
-    d = descriptor(n, nb, _ld_of(a_orig))
+    d = descriptor(n, nb, _ld_of(a_orig), isrc, jsrc)
     f = getattr(lib(), f"dlaf_b200_check_cholesky_{type_char(a_orig.dtype)}")
     return f(ctx, uplo.encode(), a_orig.ctypes.data, factor.ctypes.data, d)
+
+
+def check_cholesky_device(ctx: int, uplo: str, a_dev: int, f_dev: int, dtype, n: int, nb: int, ld: int, stream: int = 0,
+                          isrc: int = 0, jsrc: int = 0) -> float:
+    """Same check on DEVICE-resident local parts (pointers as integers); synchronises `stream`."""
+    d = descriptor(n, nb, ld, isrc, jsrc)
+    f = getattr(lib(), f"dlaf_b200_check_cholesky_device_{type_char(dtype)}")
+    return f(ctx, uplo.encode(), ctypes.c_void_p(a_dev), ctypes.c_void_p(f_dev), d, ctypes.c_void_p(stream))
 
 
 def grid_barrier(ctx: int) -> None:

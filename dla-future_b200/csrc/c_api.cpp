@@ -291,17 +291,21 @@ void copy_triangle(bool to_device, bool upper, const UserGeom& u, D* host, long 
   }
 }
 
+// LAPACK info over the grid = the FIRST non-positive-definite leading minor, i.e. the smallest non-zero per-rank value:
+// after a failure at step k the trailing updates are poisoned and later diagonal tiles on other ranks may fail at
+// larger indices. 0 (success) is mapped to INT_MAX for an ncclMin reduction.
 int reduce_info(GridCtx& c, int info, cudaStream_t s) {
   CommGrid& g = *c.grid;
   if (g.P * g.Q == 1 || g.grid_comm == nullptr)
     return info;
   if (!c.d_red)
-    DLAF_CUDA_CHECK(cudaMalloc(&c.d_red, sizeof(int)));
-  DLAF_CUDA_CHECK(cudaMemcpyAsync(c.d_red, &info, sizeof(int), cudaMemcpyHostToDevice, s));
-  DLAF_NCCL_CHECK(ncclAllReduce(c.d_red, c.d_red, 1, ncclInt32, ncclMax, g.grid_comm, s));
-  DLAF_CUDA_CHECK(cudaMemcpyAsync(&info, c.d_red, sizeof(int), cudaMemcpyDeviceToHost, s));
+    DLAF_CUDA_CHECK(cudaMalloc(&c.d_red, 2 * sizeof(int)));
+  int v = (info == 0) ? INT_MAX : info;
+  DLAF_CUDA_CHECK(cudaMemcpyAsync(c.d_red, &v, sizeof(int), cudaMemcpyHostToDevice, s));
+  DLAF_NCCL_CHECK(ncclAllReduce(c.d_red, c.d_red, 1, ncclInt32, ncclMin, g.grid_comm, s));
+  DLAF_CUDA_CHECK(cudaMemcpyAsync(&v, c.d_red, sizeof(int), cudaMemcpyDeviceToHost, s));
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-  return info;
+  return v == INT_MAX ? 0 : v;
 }
 
 // Host entry point: H2D of the referenced triangle, factorization, D2H (the reference's MatrixMirror
@@ -397,16 +401,50 @@ void pxpotrf(char uplo, int n, T* a, int ia, int ja, const int desca[9], int* in
     *info = r;
 }
 
+// The miniapp's result check on the grid of ctx (collective): see PotrfEngine<T>::residual (engine_check.cu).
+// a_dev / f_dev: DEVICE pointers to this rank's local parts in the user's layout.
+template <class T>
+double check_cholesky_device(int ctx, char uplo, const T* a_dev, const T* f_dev, const DLAF_descriptor& desc,
+                             cudaStream_t s) {
+  using D = devtype_t<T>;
+  ensure_device();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return -1.0;
+  const bool upper = is_upper(uplo);
+  const UserGeom u = user_geometry(*c.grid, desc);
+  auto& slot = get_engine<T>(c, desc, u, upper);
+  return slot.eng->residual(reinterpret_cast<const D*>(a_dev), desc.ld, reinterpret_cast<const D*>(f_dev), desc.ld, upper,
+                            c.grid->grid_comm, s);
+}
+
+// Host flavour: both local parts are staged on the device first (whole local matrices, like the reference's
+// MatrixMirror), then checked there.
 template <class T>
 double check_cholesky(int ctx, char uplo, const T* a, const T* f, const DLAF_descriptor& desc) {
   using D = devtype_t<T>;
   ensure_device();
   GridCtx& c = grid_from_context(ctx);
-  if (c.grid->P * c.grid->Q != 1)
-    return -1.0;  // distributed check: not provided
-  is_upper(uplo);
-  return check_cholesky_single_rank<D>(uplo, desc.n, desc.nb, reinterpret_cast<const D*>(a), desc.ld,
-                                       reinterpret_cast<const D*>(f), desc.ld);
+  if (!c.grid->in_grid)
+    return -1.0;
+  const UserGeom u = user_geometry(*c.grid, desc);
+  cudaStream_t s = ctx_stream(c);
+  D *da = nullptr, *df = nullptr;
+  const long lds = round_up(std::max<long>(u.lrows, 1), 2);
+  if (u.lrows > 0 && u.lcols > 0) {
+    DLAF_CUDA_CHECK(cudaMalloc(&da, sizeof(D) * lds * u.lcols));
+    DLAF_CUDA_CHECK(cudaMalloc(&df, sizeof(D) * lds * u.lcols));
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(da, sizeof(D) * lds, a, sizeof(D) * desc.ld, sizeof(D) * u.lrows, u.lcols,
+                                      cudaMemcpyHostToDevice, s));
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(df, sizeof(D) * lds, f, sizeof(D) * desc.ld, sizeof(D) * u.lrows, u.lcols,
+                                      cudaMemcpyHostToDevice, s));
+  }
+  DLAF_descriptor dd = desc;
+  dd.ld = static_cast<int>(lds);
+  const double r = check_cholesky_device<T>(ctx, uplo, reinterpret_cast<const T*>(da), reinterpret_cast<const T*>(df), dd, s);
+  cudaFree(da);
+  cudaFree(df);
+  return r;
 }
 
 template <class T>
@@ -493,12 +531,26 @@ void dlaf_free_all_grids(void) noexcept {
 }
 
 char grid_ordering(DLAF_Comm comm, int nprow, int npcol, int myprow, int mypcol) noexcept {
+  // src/c_api/grid.cpp:50-74: both predicates are AND-reduced over the communicator, column-major wins when both
+  // hold, neither -> error exit.
   const Comm* c = comm;
   const int rank = c ? c->rank : 0;
-  const bool row_major = (rank == myprow * npcol + mypcol);
-  const bool col_major = (rank == mypcol * nprow + myprow);
-  (void) col_major;
-  return row_major ? 'R' : 'C';
+  int flags[2] = {rank == myprow * npcol + mypcol ? 1 : 0, rank == mypcol * nprow + myprow ? 1 : 0};
+  if (c != nullptr && c->nccl != nullptr && c->size > 1) {
+    ensure_device();
+    int* d = nullptr;
+    DLAF_CUDA_CHECK(cudaMalloc(&d, sizeof(flags)));
+    DLAF_CUDA_CHECK(cudaMemcpy(d, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    DLAF_NCCL_CHECK(ncclAllReduce(d, d, 2, ncclInt32, ncclMin, c->nccl, nullptr));
+    DLAF_CUDA_CHECK(cudaMemcpy(flags, d, sizeof(flags), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+  }
+  // (geometry-only communicators, dlaf_b200_comm_create_local, cannot communicate: the answer is the local one)
+  if (!flags[0] && !flags[1]) {
+    std::fprintf(stderr, "Grid layout must be row major or column major.\n");
+    std::exit(-1);
+  }
+  return flags[1] ? 'C' : 'R';
 }
 
 struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int i, const int j,
@@ -528,6 +580,10 @@ struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int 
   double dlaf_b200_check_cholesky_##sfx(int ctx, char uplo, const T* a, const T* f,                           \
                                         struct DLAF_descriptor d) noexcept {                                  \
     return check_cholesky<T>(ctx, uplo, a, f, d);                                                             \
+  }                                                                                                           \
+  double dlaf_b200_check_cholesky_device_##sfx(int ctx, char uplo, const T* a_dev, const T* f_dev,            \
+                                               struct DLAF_descriptor d, void* stream) noexcept {             \
+    return check_cholesky_device<T>(ctx, uplo, a_dev, f_dev, d, static_cast<cudaStream_t>(stream));           \
   }
 
 DLAF_B200_DEFINE(d, double)

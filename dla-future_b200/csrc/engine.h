@@ -90,6 +90,14 @@ public:
 
   long launches() const { return launches_; }  // kernels launched by the last factorize()
 
+  // Result check of the miniapp on THIS grid (collective; engine_check.cu): max|A - F F^H| / max|A| over the referenced
+  // triangle of the global matrix (reference: check_cholesky, miniapp/miniapp_cholesky.cpp:408-446, which rebuilds
+  // L L^H tile by tile on the host and reduces the two max norms with MPI). a_user / f_user are DEVICE pointers to this
+  // rank's local parts (original matrix / factor) in the user's layout (transposed = user holds the upper triangle).
+  // Independent of the factorization's engines: plain native GEMMs (fp64: DMMA) on panel copies broadcast with NCCL.
+  double residual(const T* a_user, long lda, const T* f_user, long ldf, bool transposed, ncclComm_t grid_comm,
+                  cudaStream_t s);
+
   // Per-launch timing of the dominant kernel (the bulk trailing update on stream L) with CUDA events on
   // its own stream: enable before factorize(), read after the stream has been synchronised.
   void set_profiling(bool on) { profiling_ = on; }

@@ -42,9 +42,4 @@ void launch_pad_identity(T* slab, const LayoutParams& p, cudaStream_t s);
 template <class T>
 void launch_pack_panel(const T* src, long ld, T* dst, int nbp, int ntiles, cudaStream_t s);
 
-// miniapp result check on a single-rank grid (check.cu): max|A - F F^H| / max|A| over the `uplo` triangle,
-// a and f are HOST pointers (column-major).
-template <class T>
-double check_cholesky_single_rank(char uplo, long n, int nb, const T* a_host, long lda, const T* f_host, long ldf);
-
 }  // namespace dlaf_b200

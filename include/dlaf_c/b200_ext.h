@@ -44,13 +44,18 @@ DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_d(int ctx, d
 DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_c(int ctx, dlaf_complex_c* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
 DLAF_EXTERN_C void dlaf_b200_set_random_hermitian_positive_definite_z(int ctx, dlaf_complex_z* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
 
-/* The miniapp's result check: max|A - L L^H| / max|A| over the `uplo` triangle, evaluated on the GPU
- * (a_orig and factor are HOST pointers to the local = global matrix). Single-rank grids; returns -1 on a
- * distributed grid. */
+/* The miniapp's result check (miniapp/miniapp_cholesky.cpp:408-446): max|A - L L^H| / max|A| over the `uplo` triangle of the
+ * GLOBAL matrix, evaluated on the GPUs of the grid. Collective over the grid of ctx; every rank passes its local parts
+ * (a_orig = the input, factor = the result; HOST pointers, same descriptor) and receives the same value (-1 on ranks
+ * outside the grid). The _device_ flavour takes DEVICE pointers (synchronises `cuda_stream`). */
 DLAF_EXTERN_C double dlaf_b200_check_cholesky_s(int ctx, char uplo, const float* a_orig, const float* factor, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
 DLAF_EXTERN_C double dlaf_b200_check_cholesky_d(int ctx, char uplo, const double* a_orig, const double* factor, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
 DLAF_EXTERN_C double dlaf_b200_check_cholesky_c(int ctx, char uplo, const dlaf_complex_c* a_orig, const dlaf_complex_c* factor, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
 DLAF_EXTERN_C double dlaf_b200_check_cholesky_z(int ctx, char uplo, const dlaf_complex_z* a_orig, const dlaf_complex_z* factor, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C double dlaf_b200_check_cholesky_device_s(int ctx, char uplo, const float* a_dev, const float* factor_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C double dlaf_b200_check_cholesky_device_d(int ctx, char uplo, const double* a_dev, const double* factor_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C double dlaf_b200_check_cholesky_device_c(int ctx, char uplo, const dlaf_complex_c* a_dev, const dlaf_complex_c* factor_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C double dlaf_b200_check_cholesky_device_z(int ctx, char uplo, const dlaf_complex_z* a_dev, const dlaf_complex_z* factor_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
 /* Barrier over the ranks of the grid (the miniapp's MPI_Barrier / wait_all_communicators). */
 DLAF_EXTERN_C void dlaf_b200_grid_barrier(int ctx) DLAF_NOEXCEPT;
 

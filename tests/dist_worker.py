@@ -111,6 +111,20 @@ def main():
                             ok, msg = False, "unreferenced triangle modified"
                     if info != 0 or not ok:
                         failures.append((n, nb, t, uplo, s, info, msg))
+                    if n > 64:
+                        # the miniapp's result check on the grid (collective; miniapp_cholesky.cpp:408-446): same value on
+                        # every rank, below the eps*n gate, and it must see a corrupted factor
+                        res = pkg.check_cholesky(ctx, uplo, orig, loc, nb, n=n, isrc=s[0], jsrc=s[1])
+                        gate = O.residual_gate(dt, n)[0]
+                        if not (0 <= res <= gate):
+                            failures.append(("grid residual", n, nb, t, uplo, s, res, gate))
+                        if (n, nb, t) == (1000, 128, "d"):
+                            bad = loc.copy(order="F")
+                            if (myrow, mycol) == (0, 0):
+                                bad[0, 0] += 0.5
+                            res_bad = pkg.check_cholesky(ctx, uplo, orig, bad, nb, n=n, isrc=s[0], jsrc=s[1])
+                            if not res_bad > 1e-6:
+                                failures.append(("grid residual blind", res_bad))
         # non-SPD: every rank must report the same LAPACK info
         n, nb = 300, 64
         B = np.eye(n, order="F") * 4.0
@@ -122,6 +136,19 @@ def main():
         info = pkg.cholesky_factorization(ctx, "L", loc, nb, n=n)
         if rank < P * Q and info != 201:
             failures.append(("info", info))
+        # dense indefinite matrix: after the first failure the trailing updates are poisoned and LATER diagonal tiles
+        # (on other ranks) fail too -> the grid must report the FIRST failing leading minor, like LAPACK on one process
+        n, nb = 700, 64
+        D = O.set_random_hermitian_positive_definite(n, nb, np.float64)
+        D[325, 325] = -3.0
+        want = O.cholesky_local("L", D.copy(order="F"), nb, 4)
+        if rank < P * Q:
+            loc = np.asfortranarray(O.scatter_block_cyclic(D, nb, (P, Q), (0, 0))[(myrow, mycol)])
+        else:
+            loc = np.zeros((1, 1), order="F")
+        info = pkg.cholesky_factorization(ctx, "L", loc, nb, n=n)
+        if rank < P * Q and (want != 326 or info != want):
+            failures.append(("info dense indefinite", info, want))
     flag = torch.tensor([len(failures)], dtype=torch.int64, device="cuda" if a.mode == "gpu" else "cpu")
     dist.all_reduce(flag)
     if failures:

@@ -128,3 +128,60 @@ def test_large_property_residual(pkg, oracle, grid11):
     tol = oracle.cholesky_tolerance(n, np.float64)
     ok, _, msg = oracle.check_near(np.tril(ref), np.tril(out), tol, tol)
     assert ok, msg
+
+
+def test_dense_indefinite_reports_first_failing_minor(pkg, oracle, grid11):
+    """A dense matrix that stops being positive definite in the middle: info = order of the FIRST non-positive
+    leading minor (what LAPACK's potrf reports; the oracle's tile loop returns the same)."""
+    n, nb = 700, 64
+    a = oracle.set_random_hermitian_positive_definite(n, nb, np.float64)
+    a[325, 325] = -3.0
+    want = oracle.cholesky_local("L", a.copy(order="F"), nb)
+    assert want == 326
+    assert pkg.cholesky_factorization(grid11, "L", a.copy(order="F"), nb) == want
+    assert pkg.cholesky_factorization(grid11, "U", a.copy(order="F"), nb) == want
+
+
+@pytest.mark.parametrize("t,n,nb,uplo", [("d", 1024, 256, "L"), ("d", 777, 100, "U"), ("z", 512, 128, "L"),
+                                         ("s", 640, 128, "U"), ("c", 300, 96, "L")])
+def test_grid_residual_check_matches_oracle_residual(pkg, oracle, grid11, t, n, nb, uplo):
+    """The product's result check (engine_check.cu, the distributed restatement of miniapp_cholesky.cpp:408-446) against
+    the oracle's residual of the same factor: same max-norm ratio up to rounding of the two evaluations; a corrupted
+    factor is seen."""
+    dt = pkg.TYPES[t]
+    a = oracle.set_random_hermitian_positive_definite(n, nb, dt)
+    f = a.copy(order="F")
+    assert pkg.cholesky_factorization(grid11, uplo, f, nb) == 0
+    r_gpu = pkg.check_cholesky(grid11, uplo, a, f, nb)
+    r_cpu = oracle.residual(uplo, a, f)
+    gate = oracle.residual_gate(dt, n)[0]
+    assert 0 <= r_gpu <= gate and r_cpu <= gate
+    assert abs(r_gpu - r_cpu) <= 0.5 * max(r_gpu, r_cpu) + 1e-3 * gate, (r_gpu, r_cpu)
+    g = f.copy(order="F")
+    g[n // 2, n // 3 if uplo == "L" else n // 2 + 5] += 0.25
+    assert pkg.check_cholesky(grid11, uplo, a, g, nb) > 100 * gate
+
+
+def test_baseline_config_size_elementwise_vs_oracle(pkg, oracle, grid11):
+    """BASELINE config C2 (fp64 N=16384 nb=512, one GPU) compared ELEMENT-WISE with the reference algorithm's factor at the
+    reference's unit-test tolerance, not only through the residual (the oracle needs ~10-20 s of host time)."""
+    n, nb = 16384, 512
+    a = np.zeros((n, n), dtype=np.float64, order="F")
+    pkg.set_random_hermitian_positive_definite(grid11, a, n, nb)
+    out = a.copy(order="F")
+    assert pkg.cholesky_factorization(grid11, "L", out, nb) == 0
+    ref = a  # factor the input in place on the CPU (saves 2 GB)
+    assert oracle.cholesky_local("L", ref, nb, nthreads=oracle.max_pool_threads()) == 0
+    tol = oracle.cholesky_tolerance(n, np.float64)
+    bs = 2048
+    for j0 in range(0, n, bs):  # block columns of the lower triangle
+        e = np.tril(ref[j0:, j0:j0 + bs], 0) if j0 == 0 else ref[j0:, j0:j0 + bs].copy()
+        v = out[j0:, j0:j0 + bs].copy()
+        if j0:
+            iu = np.triu_indices(bs, 1)
+            e[iu] = 0
+            v[iu] = 0
+        else:
+            v = np.tril(v, 0)
+        ok, _, msg = oracle.check_near(e, v, tol, tol)
+        assert ok, f"block column {j0}: {msg}"

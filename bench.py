@@ -422,7 +422,9 @@ def run_ours(args):
     engine = os.environ.get("DLAF_B200_D_BULK", "ozaki")
     peak64 = pkg.measure_fp64_tensor_peak_tflops()
     achieved64 = (prof_fl / (prof_ms * 1e-3) / 1e12) if prof_ms > 0 else None
-    cap_file = "r01_ncu_ozaki_bulk.json" if engine == "ozaki" else "r01_ncu_gemm_bulk_final.json"
+    cap_file = "r02_ncu_ozaki_bulk.json" if engine == "ozaki" else "r01_ncu_gemm_bulk_final.json"
+    if args.type != "d":
+        engine = {"s": "tf32x3", "c": "simt", "z": "zdmma"}[args.type]
     traffic, traffic_note = None, None
     try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture (one launch)
         with open(os.path.join(ROOT, "profiles", cap_file)) as f:
@@ -434,13 +436,16 @@ def run_ours(args):
         pass
     if engine == "ozaki":
         peak8 = pkg.measure_int8_tensor_peak_tops()
-        achieved8 = achieved64 * 36.0 if achieved64 else None
+        pairs = pkg.ozaki_pairs()
+        achieved8 = achieved64 * pairs if achieved64 else None
         roofline = {
-            "kernel": "gemm_ozaki_i8_kernel (bulk trailing update, stream L): fp64 C -= A B^T as 36 exact int8 tcgen05 MMAs",
+            "kernel": f"gemm_ozaki_i8_kernel<32> (bulk trailing update, stream L): fp64 C -= A B^T as {pairs} exact int8 tcgen05 digit-plane products",
             "bound": "tensor", "achieved": achieved8, "peak": peak8, "unit": "TFLOP/s",
             "frac": (achieved8 / peak8) if achieved8 else None,
-            "unit_note": "int8 tensor-core tera-ops/s (1 MAC = 2 ops); algorithmic ops per launch = 36 x the fp64 flops of "
-                         "the update (8 x 7-bit digits, digit pairs t + u < 8)",
+            "unit_note": f"int8 tensor-core tera-ops/s (1 MAC = 2 ops); algorithmic ops per launch = {pairs} x the fp64 flops of "
+                         "the update (7 balanced radix-256 digits, digit pairs t + u <= 6; round 1 used 36)",
+            "int8_macs_per_fp64_mac": pairs,
+            "guard_fallback_steps_last_run": pkg.guard_fallback_steps(ctx),
             "fp64_equivalent_tflops": achieved64, "fp64_tensor_peak_tflops": peak64,
             "frac_of_fp64_tensor_roofline": (achieved64 / peak64) if achieved64 else None,
             "traffic": traffic, "traffic_note": traffic_note,
@@ -448,11 +453,29 @@ def run_ours(args):
                            "(dlaf_b200_measure_int8_tensor_peak_tops); MEASURED_PEAKS.json holds bf16 (1639 TF/s burst) and "
                            "HBM only; nominal B200 int8 dense = 4500 TOP/s. fp64 tensor (DMMA) peak measured the same way.",
         }
+    elif engine == "tf32x3":
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak_tf32 = peaks.get("bf16_tflops", 2250.0) / 2.0  # tf32 dense = half the bf16 rate on tcgen05
+        ach = achieved64 * 3.0 if achieved64 else None
+        roofline = {
+            "kernel": "gemm_tf32x3_kernel (bulk trailing update, stream L): fp32 C -= A B^T as 3 tcgen05 kind::tf32 MMAs (hi*hi, hi*lo, lo*hi)",
+            "bound": "tensor", "achieved": ach, "peak": peak_tf32, "unit": "TFLOP/s", "frac": (ach / peak_tf32) if ach else None,
+            "fp32_equivalent_tflops": achieved64, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (tf32 runs at half the bf16 rate); nominal fallback 1125",
+        }
     else:
         roofline = {
-            "kernel": "gemm_nt_f64_kernel<GemmCfg<64,64,16,3,4,2,2>> (bulk trailing update, stream L)", "bound": "tensor",
-            "achieved": achieved64, "peak": peak64, "unit": "TFLOP/s", "frac": (achieved64 / peak64) if achieved64 else None,
-            "traffic": traffic, "traffic_note": traffic_note,
+            "kernel": {"dmma": "gemm_nt_f64_kernel<GemmCfg<64,64,16,3,4,2,2>>", "zdmma": "gemm_nt_z_kernel (complex128 on DMMA)",
+                       "simt": "gemm_nt_simt_kernel<float2>"}.get(engine, engine) + " (bulk trailing update, stream L)",
+            "bound": "tensor" if engine != "simt" else "fp32 FMA pipe",
+            "achieved": achieved64, "peak": peak64 if engine != "simt" else None, "unit": "TFLOP/s",
+            "frac": (achieved64 / peak64) if (achieved64 and engine != "simt") else None,
+            "traffic": traffic if engine == "dmma" else None, "traffic_note": traffic_note if engine == "dmma" else None,
             "peak_source": "measured now on this GPU: DMMA.8x8x4 issue-rate microbenchmark (dlaf_b200_measure_fp64_tensor_peak_tflops); "
                            "MEASURED_PEAKS.json holds no fp64 figure (bf16 cuBLAS + HBM copy only); nominal B200 fp64 = 40 TFLOP/s",
         }
@@ -548,15 +571,18 @@ def run_ours(args):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC if (args.type, n, nb) == ("d", 32768, 512) else f"POTRF GFLOP/s ({args.type}, N={n}, nb={nb})",
+            "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "dtype_note": ("fp64 in, fp64 out; panels (POTRF/TRSM) in native fp64 DMMA; trailing update = exact int8 digit products "
-                           "(8 x 7-bit digits per operand, int32 accumulation, fp64 recombination) whose error is BELOW a native "
-                           "fp64 GEMM (tools/gpu_ozaki_test: 2.9e-17 vs 3.9e-16 of sum|a||b|)") if os.environ.get("DLAF_B200_D_BULK", "ozaki") == "ozaki" else "native fp64 (DMMA)",
-            "config": {"workload": f"fp64 POTRF N={n} nb={nb} uplo=L, grid {P}x{Q} (ColumnMajor), device-resident, in place",
+            "dtype": {"s": "f32", "d": "f64", "c": "c64", "z": "c128"}[args.type], "data": "synthetic",
+            "dtype_note": (("fp64 in, fp64 out; panels (POTRF/TRSM) in native fp64 DMMA; trailing update = exact int8 digit products "
+                            "(7 balanced radix-256 digits of a 55-bit row mantissa, int32 accumulation, exact recombination; error model "
+                            "and data-dependent native-fp64 fallback: dla-future_b200/csrc/gemm_ozaki.h)")
+                           if os.environ.get("DLAF_B200_D_BULK", "ozaki") == "ozaki" else "native fp64 (DMMA)") if args.type == "d"
+            else {"s": "fp32 in/out; trailing update 3xTF32 on tcgen05", "c": "complex64, SIMT", "z": "complex128, DMMA"}[args.type],
+            "config": {"workload": f"{ {'s': 'fp32', 'd': 'fp64', 'c': 'complex64', 'z': 'complex128'}[args.type] } POTRF N={n} nb={nb} uplo=L, grid {P}x{Q} (ColumnMajor), device-resident, in place",
                        "input": "set_random_hermitian_positive_definite (miniapp generator), restored before every step",
-                       "l2": "matrix (%.1f GB per GPU) is larger than L2; every step starts from a fresh copy" % (lr * lc * 8 / 1e9),
+                       "l2": "matrix (%.1f GB per GPU) is larger than L2; every step starts from a fresh copy" % (lr * lc * itemsize / 1e9),
                        "timing": "CUDA events on the launching stream per step, summed over K steps, max over ranks",
                        "wall_s_incl_restore": wall},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

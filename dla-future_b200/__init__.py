@@ -34,7 +34,8 @@ C_API_SYMBOLS = [
     *[f"dlaf_b200_set_random_hermitian_positive_definite_{t}" for t in "sdcz"],
     *[f"dlaf_b200_check_cholesky_{t}" for t in "sdcz"], *[f"dlaf_b200_check_cholesky_device_{t}" for t in "sdcz"],
     "dlaf_b200_grid_barrier",
-    "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info",
+    "dlaf_b200_wait", "dlaf_b200_last_launch_count", "dlaf_b200_grid_info", "dlaf_b200_guard_fallback_steps",
+    "dlaf_b200_ozaki_pairs",
     "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops", "dlaf_b200_measure_int8_tensor_peak_tops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
 ]
@@ -139,6 +140,9 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_grid_barrier.restype = None
     L.dlaf_b200_wait.argtypes = [ci, vp]
     L.dlaf_b200_wait.restype = ci
+    L.dlaf_b200_guard_fallback_steps.argtypes = [ci]
+    L.dlaf_b200_guard_fallback_steps.restype = ci
+    L.dlaf_b200_ozaki_pairs.restype = ci
     L.dlaf_b200_last_launch_count.argtypes = [ci]
     L.dlaf_b200_last_launch_count.restype = ctypes.c_long
     L.dlaf_b200_set_profiling.argtypes = [ci, ci]
@@ -268,6 +272,15 @@ def wait(ctx: int, stream: int = 0) -> int:
 
 def last_launch_count(ctx: int) -> int:
     return lib().dlaf_b200_last_launch_count(ctx)
+
+
+def guard_fallback_steps(ctx: int) -> int:
+    """Steps of the last fp64 factorization whose update fell back from the int8-digit engine to native fp64 (-1: n/a)."""
+    return lib().dlaf_b200_guard_fallback_steps(ctx)
+
+
+def ozaki_pairs() -> int:
+    return lib().dlaf_b200_ozaki_pairs()
 
 
 def set_profiling(ctx: int, enable: bool) -> None:

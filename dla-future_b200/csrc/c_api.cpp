@@ -41,6 +41,7 @@ struct EngineSlotBase {
   virtual void set_profiling(bool on) = 0;
   virtual void read_profile(double out[3]) = 0;
   virtual void read_chain_profile(double out[6]) = 0;
+  virtual int guard_fallback_steps() const = 0;
 };
 
 template <class D>
@@ -67,6 +68,7 @@ struct EngineSlot : EngineSlotBase {
     if (eng)
       eng->read_chain_profile(out);
   }
+  int guard_fallback_steps() const override { return eng ? eng->guard_fallback_steps() : -1; }
   D* ensure_stage(size_t elems) {
     if (elems > stage_elems) {
       cudaFree(stage);
@@ -605,6 +607,17 @@ long dlaf_b200_last_launch_count(int ctx) noexcept {
   if (c.last_type < 0 || !c.slot[c.last_type])
     return 0;
   return c.slot[c.last_type]->launches();
+}
+
+int dlaf_b200_guard_fallback_steps(int ctx) noexcept {
+  GridCtx& c = grid_from_context(ctx);
+  if (c.last_type < 0 || !c.slot[c.last_type])
+    return -1;
+  return c.slot[c.last_type]->guard_fallback_steps();
+}
+
+int dlaf_b200_ozaki_pairs(void) noexcept {
+  return kOzakiPairs;
 }
 
 void dlaf_b200_grid_barrier(int ctx) noexcept {

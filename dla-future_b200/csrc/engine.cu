@@ -95,6 +95,12 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
     use_ozaki_ = want && nt_ > 1 && ltr_ > 0 && ltc_ > 0 && nbp_ <= 512;
     const char* sc = std::getenv("DLAF_B200_SPLIT_CHAIN");
     split_chain_ = use_ozaki_ && geo_.P * geo_.Q == 1 && (sc == nullptr || std::atoi(sc) != 0);
+    if (use_ozaki_) {
+      DLAF_CUDA_CHECK(cudaMalloc(&oz_flag_, sizeof(int) * nt_));
+      DLAF_CUDA_CHECK(cudaMallocHost(&h_oz_flags_, sizeof(int) * nt_));
+      for (int k = 0; k < nt_; ++k)
+        h_oz_flags_[k] = 0;
+    }
     if (use_ozaki_)
       for (int i = 0; i < 2; ++i) {
         osplit_[i].allocate(static_cast<long>(ltr_) * nbp_, nbp_);
@@ -164,6 +170,8 @@ PotrfEngine<T>::~PotrfEngine() {
       osplitT_[i].release();
     }
   }
+  cudaFree(oz_flag_);
+  cudaFreeHost(h_oz_flags_);
   cudaFree(own_slab_);
   cudaFree(d_info_);
   cudaFreeHost(h_info_);
@@ -461,7 +469,7 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
           wait_bulk(k - 2, -1, sR_);
         DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evT1_[slot], 0));
         if constexpr (std::is_same_v<T, double>) {
-          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sR_);
+          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sR_, 0, 0, oz_flag_ + k);
           ++launches_;
         }
       }
@@ -483,7 +491,7 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       }
       if constexpr (std::is_same_v<T, double>) {
         if (use_ozaki_ && k < nt_ - 1 && P * Q == 1) {
-          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sH_);
+          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sH_, 0, 0, oz_flag_ + k);
           ++launches_;
         }
       }
@@ -536,11 +544,12 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
   if constexpr (std::is_same_v<T, double>) {
     if (use_ozaki_ && k < nt_ - 1 && P * Q > 1) {
       if (mt > 0) {
-        osplit_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sH_, nbp_, static_cast<long>(tsz));
+        osplit_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sH_, nbp_, static_cast<long>(tsz), oz_flag_ + k);
         ++launches_;
       }
       if (P > 1 && ltc_ - lj1 > 0) {
-        osplitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sH_, nbp_, static_cast<long>(tsz));
+        osplitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sH_, nbp_, static_cast<long>(tsz),
+                             oz_flag_ + k);
         ++launches_;
       }
     }
@@ -637,12 +646,16 @@ void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows
   if constexpr (std::is_same_v<T, double>) {
     if (use_ozaki_ && !native) {
       const long a_row = static_cast<long>(ri0 - li1) * nbp_;
+      const int* guard = oz_flag_ + k;
       if (P > 1)
-        launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplitT_[slot], static_cast<long>(cj0 - lj1) * nbp_, st);
+        launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplitT_[slot], static_cast<long>(cj0 - lj1) * nbp_, st, 0, guard);
       else
         launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplit_[slot], static_cast<long>(gj0 - (k + 1)) * nbp_, st,
-                             static_cast<long>(Q) * nbp_);
-      ++launches_;
+                             static_cast<long>(Q) * nbp_, guard);
+      // guard raised by the digit split of this step's panel: the same update on the native fp64 kernel (otherwise
+      // a handful of CTAs that read the flag and leave)
+      launch_gemm_nt_f64_if(a, guard, st);
+      launches_ += 2;
       return;
     }
   }
@@ -860,6 +873,11 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, ev_start_, 0));
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(sL_, ev_start_, 0));
   DLAF_CUDA_CHECK(cudaMemsetAsync(d_info_, 0, sizeof(int), sH_));
+  if (oz_flag_ != nullptr) {
+    DLAF_CUDA_CHECK(cudaMemsetAsync(oz_flag_, 0, sizeof(int) * nt_, sH_));
+    DLAF_CUDA_CHECK(cudaEventRecord(evF_[0], sH_));  // the split of step 0 may run on stream R
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evF_[0], 0));
+  }
 
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, ev_start_, 0));
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, ev_start_, 0));
@@ -960,6 +978,18 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evC_[(nt_ - 2) % 2], 0));
   }
   DLAF_CUDA_CHECK(cudaMemcpyAsync(h_info_, d_info_, sizeof(int), cudaMemcpyDeviceToHost, s));
+  if (oz_flag_ != nullptr)
+    DLAF_CUDA_CHECK(cudaMemcpyAsync(h_oz_flags_, oz_flag_, sizeof(int) * nt_, cudaMemcpyDeviceToHost, s));
+}
+
+template <class T>
+int PotrfEngine<T>::guard_fallback_steps() const {
+  if (h_oz_flags_ == nullptr)
+    return -1;
+  int c = 0;
+  for (int k = 0; k < nt_; ++k)
+    c += h_oz_flags_[k] != 0;
+  return c;
 }
 
 template <class T>

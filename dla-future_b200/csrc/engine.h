@@ -89,6 +89,9 @@ public:
   int info(cudaStream_t s);
 
   long launches() const { return launches_; }  // kernels launched by the last factorize()
+  // Steps of the last factorize() whose trailing update fell back from the int8-digit engine to native fp64 because the
+  // guard fired (valid after info()); -1 when the int8 engine is not in use.
+  int guard_fallback_steps() const;
 
   // Result check of the miniapp on THIS grid (collective; engine_check.cu): max|A - F F^H| / max|A| over the referenced
   // triangle of the global matrix (reference: check_cholesky, miniapp/miniapp_cholesky.cpp:408-446, which rebuilds
@@ -166,6 +169,10 @@ private:
   bool use_ozaki_ = false;
   OzakiSplit osplit_[2];
   OzakiSplit osplitT_[2];
+  // guard of the int8 engine (gemm_ozaki.h): one device flag per step, raised by the digit split of that step's panel
+  // when a row spans too many binades; the updates of a flagged step run on the native fp64 kernel instead
+  int* oz_flag_ = nullptr;      // [nt]
+  int* h_oz_flags_ = nullptr;   // pinned copy read by guard_fallback_steps()
   bool split_panels() const { return use_tf32_ || use_ozaki_; }
   // 1 x 1 grid, int8 engine: the panel of a step is finished on stream R while stream H already goes on with the next
   // diagonal tile (engine.cu: panel_step). DLAF_B200_SPLIT_CHAIN=0 keeps everything on stream H.

@@ -70,6 +70,10 @@ struct TrsmFusedArgs {
 // m % 32 == 0, 16-byte aligned operands with even leading dimensions.
 void launch_trsm_fused_f64(const TrsmFusedArgs& args, int m, cudaStream_t stream);
 
+// Native fp64 (DMMA) product executed only if *flag != 0 when the kernel starts (gemm_dmma.cu): the fallback of the
+// int8-digit trailing update when its guard fires (gemm_ozaki.h).
+void launch_gemm_nt_f64_if(const GemmArgsT<double>& args, const int* flag, cudaStream_t stream);
+
 // complex<double> flavour (gemm_zdmma.cu: trsm_fused_z_kernel), 64 x 64 diagonal blocks, m % 64 == 0.
 void launch_trsm_fused_z(double2* b, long ldb, int m, const double2* t, long ldt, const double2* w, int ns,
                          cudaStream_t stream);

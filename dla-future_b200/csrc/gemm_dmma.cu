@@ -67,6 +67,29 @@ void launch_gemm_nt_f64(const GemmArgs& a, cudaStream_t stream) {
     launch_gemm_nt_f64_cfg(a, bulk_cfg, stream);
 }
 
+void launch_gemm_nt_f64_if(const GemmArgs& a, const int* flag, cudaStream_t stream) {
+  using Cfg = GemmCfg64w4s3;
+  if (a.M <= 0 || a.N <= 0)
+    return;
+  DLAF_B200_ASSERT(a.M % Cfg::BM == 0 && a.N % Cfg::BN == 0 && a.K % Cfg::BK == 0 && a.K > 0 && flag != nullptr,
+                   "guarded gemm shape");
+  DLAF_B200_ASSERT(a.lda % 2 == 0 && a.ldb % 2 == 0 && a.ldc % 2 == 0 && a.a_ts % 2 == 0 && a.b_ts % 2 == 0,
+                   "16-byte aligned operand columns");
+  static int ctas = 0;
+  if (ctas == 0) {
+    DLAF_CUDA_CHECK(cudaFuncSetAttribute(gemm_nt_f64_if_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    int dev = 0, nsm = 0;
+    DLAF_CUDA_CHECK(cudaGetDevice(&dev));
+    DLAF_CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    ctas = nsm * Cfg::MINB;
+  }
+  const long tiles = static_cast<long>(a.M / Cfg::BM) * (a.N / Cfg::BN);
+  const unsigned grid = static_cast<unsigned>(tiles < ctas ? tiles : ctas);
+  gemm_nt_f64_if_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a, flag);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_trsm_fused_f64(const TrsmFusedArgs& a, int m, cudaStream_t stream) {
   using Cfg = GemmCfg32x128w4;
   if (m <= 0 || a.ns <= 0)

@@ -257,6 +257,36 @@ __global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_kernel(co
   gemm_nt_f64_tile<Cfg>(t, smem);
 }
 
+// Guarded flavour of the same GEMM: runs only when *flag != 0, on a persistent-style grid (a few CTAs per SM looping over
+// the tiles) so that the usual case — flag clear, the int8-digit kernel did the update — costs one tiny launch.
+// This is the native-fp64 fallback of the int8 trailing update (gemm_ozaki.h: guard).
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB) gemm_nt_f64_if_kernel(const GemmArgs p, const int* flag) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK;
+  extern __shared__ __align__(16) double smem[];
+  if (*flag == 0)
+    return;
+  const int gx = p.M / BM, gy = p.N / BN;
+  for (int l = blockIdx.x; l < gx * gy; l += gridDim.x) {
+    const int row0 = (l % gx) * BM, col0 = (l / gx) * BN;
+    GemmTileOp t;
+    t.cls = classify_tile(p, row0, col0, BM, BN, t.grow0, t.gcol0);
+    if (t.cls == 0)
+      continue;
+    t.Ag = p.A + (p.a_ts ? (row0 / p.nbp) * p.a_ts + row0 % p.nbp : row0);
+    t.lda = p.lda;
+    t.Bg = p.B + (p.b_ts ? (col0 / p.nbp) * p.b_ts + col0 % p.nbp : col0);
+    t.ldb = p.ldb;
+    t.Cg = p.C + row0 + static_cast<long>(col0) * p.ldc;
+    t.ldc = p.ldc;
+    t.KT = p.K / BK;
+    t.alpha = p.alpha;
+    t.beta = p.beta;
+    gemm_nt_f64_tile<Cfg>(t, smem);
+    __syncthreads();  // the staging ring is reused by the next tile
+  }
+}
+
 // Panel TRSM in ONE launch:  B <- B * L^-T  for a row panel B (m x ns*G) against the factored diagonal tile
 // L (ns*G x ns*G, lower) whose G x G diagonal blocks come pre-inverted (W, from potrf_inv). Rows are
 // independent in a right-side triangular solve, so each CTA owns BM rows of B and runs the whole block
@@ -319,6 +349,8 @@ using GemmCfg32x128w4 = GemmCfg<32, 128, 16, 3, 4, 1, 4>;  // in-place products 
 
 // Host launcher (defined in gemm_dmma.cu): picks the tile configuration.
 void launch_gemm_nt_f64(const GemmArgs& args, cudaStream_t stream);
+// Same product, executed only if *flag != 0 when the kernel starts (flag: device int).
+void launch_gemm_nt_f64_if(const GemmArgs& args, const int* flag, cudaStream_t stream);
 // Explicit configuration (tools / A-B measurements): 0 = 128x128x16x4, 1 = 64x128 (2 CTA/SM), 2 = 64x64,
 // 3 = 128x128x32x3, 4 = 128x64 (2 CTA/SM), 5 = 64x64/4 warps/3 stages (4 CTA/SM), 6 = same/4 stages (3 CTA/SM),
 // 7 = 32x128/4 warps (in-place products).

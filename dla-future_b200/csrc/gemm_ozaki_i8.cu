@@ -1,26 +1,32 @@
-// fp64 trailing update on tcgen05 via exact int8 slice products (Ozaki scheme), see gemm_ozaki.h.
+// fp64 trailing update on tcgen05 via exact int8 digit products (Ozaki scheme), see gemm_ozaki.h.
 //
 //   C(MxN, fp64, column-major) += alpha * A(MxK) B(NxK)^T          alpha = +-1, lower-triangular tile mask
 //
 // Replaces the cublasDgemm / cublasDsyrk tile calls of the reference's trailing update
 // (include/dlaf/factorization/cholesky/impl.h:69-94, include/dlaf/blas/tile.h:249-304) for the bulk (~95 % of the
-// flops) of DPOTRF, above the 37 TFLOP/s DMMA/DFMA roofline of B200: 36 int8 MMAs (t + u < 8) per fp64 product
-// at the int8 tensor rate.
+// flops) of DPOTRF, above the 37 TFLOP/s DMMA/DFMA roofline of B200: 28 int8 MMAs (digit pairs t + u <= 6) per fp64
+// product at the int8 tensor rate.
 //
-// Operands: OzakiSplit (split_i8_kernel below): 8 int8 digit planes per panel, K-major, + one power-of-two scale
-// per row. CTA = 128 x 64 tiles of C, a few consecutive ones per CTA (DLAF_B200_OZAKI_TPC); TMEM holds the 8
-// anti-diagonal group accumulators (8 x 64 columns of int32 = all 512 columns). 18 warps: warp 0 = TMA producer
-// (one lane), warp 1 = TMEM allocator + MMA issuer (one lane), warps 2..17 = epilogue (TMEM lane quadrant = warp % 4,
-// column quarter = (warp - 2) / 4).
-// Pipeline: 2 stages x {8 A planes (128 rows x 64 k), 8 B planes (64 rows x 64 k)} = 96 KB per stage, loaded by two
-// 3-D TMA boxes (k, row, plane) in SWIZZLE_64B K-major UMMA layout; 24 tcgen05.mma.kind::i8 (M128, N up to 256, K32)
-// per stage — one instruction covers up to 4 digit-plane pairs, see the issuer loop; full/empty mbarriers,
-// tcgen05.commit releases a stage / signals the epilogue, the epilogue hands TMEM back through tmem_empty. Every
-// mbarrier wait is bounded (trap instead of hang).
-// Epilogue: per row (= TMEM lane) and 4 columns at a time the 8 int32 group sums are folded EXACTLY into two 46-bit
-// integers, converted to fp64 without I2F, combined, scaled by 2^(e_row + e_col - 35) and added to the C values that
-// were fetched while the MMAs ran; coalesced column accesses; the masked variant is chosen per warp (tcgen05.ld is
-// warp-collective).
+// Operands: OzakiSplit (split_i8_kernel below): 7 balanced radix-256 digit planes per panel (int8, K-major) + one
+// power-of-two scale per row. Round 2 layout (round 1: 8 radix-128 digits, 36 pairs, 128 x 64 tiles, TMEM full):
+//   * CTA tile 128 x BN of C, BN = 32: the 7 anti-diagonal group accumulators take 7 x 32 = 224 TMEM columns, so TWO
+//     accumulator sets fit the 512 columns and the epilogue of tile i overlaps the MMAs of tile i + 1
+//     (BN = 64: one set, the round-1 structure, kept as an A/B variant: DLAF_B200_OZAKI_BN=64);
+//   * digit plane t of A meets planes u = 0 .. 6-t of B, whose accumulators are adjacent in TMEM and whose smem
+//     planes are adjacent rows -> ONE tcgen05.mma.kind::i8 with N = BN (7 - t) <= 256 per plane t: 7 MMAs per k-step;
+//   * 18 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane), warps 2..17 =
+//     epilogue (TMEM lane quadrant = warp % 4, BN / 4 columns each);
+//   * 3 stages x {7 A planes (128 rows x 64 k), 7 B planes (BN rows x 64 k)} = 70 KB per stage, two 3-D TMA boxes
+//     (k, row, plane) per stage in SWIZZLE_64B K-major UMMA layout; full/empty mbarriers per stage, tmem_full /
+//     tmem_empty per accumulator set; every mbarrier wait is bounded (trap instead of hang);
+//   * a CTA handles a few consecutive tiles (DLAF_B200_OZAKI_TPC) so that it stays short-lived next to the
+//     high-priority panel-chain kernels.
+// Epilogue: per row (= TMEM lane) the 7 int32 group sums are folded EXACTLY into two integers (< 2^48, < 2^43),
+// converted to fp64 without I2F, combined with one rounding, scaled by 2^(e_row + e_col - 38) and added to the C values
+// that were fetched while the MMAs ran; coalesced column accesses; the masked variant is chosen per warp.
+// Guard: split_i8_kernel raises a per-step flag when a nonzero entry would keep fewer than `min_bits` significant bits
+// (a row of the panel spans more than ~40 binades); this kernel then returns at once and the guarded native kernel
+// (gemm_dmma.cu: launch_gemm_nt_f64_if) performs the update in fp64 DMMA instead.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -37,17 +43,26 @@ namespace dlaf_b200 {
 namespace {
 
 constexpr int S = kOzakiSlices;
-constexpr int OBM = 128, OBN = 64, OBK = 64 /* int8 k per stage */, OSTAGES = 2;
+constexpr int OBM = 128, OBK = 64 /* int8 k per stage */;
 constexpr int A_PLANE_BYTES = OBM * OBK;  // 8 KB
-constexpr int B_PLANE_BYTES = OBN * OBK;  // 4 KB
 constexpr int A_STAGE_BYTES = S * A_PLANE_BYTES;
-constexpr int B_STAGE_BYTES = S * B_PLANE_BYTES;
-constexpr int OSTAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 96 KB
 constexpr int OEPI_WARPS = 16;
 constexpr int OTHREADS = 64 + 32 * OEPI_WARPS;  // TMA warp, MMA warp, 16 epilogue warps
-constexpr int OSMEM_BYTES = OSTAGES * OSTAGE_BYTES + 1024 /*alignment slack*/ + 2048 /*barriers + column scales*/;
 constexpr int kRowChunk = 64;  // row tiles per rasterization chunk
-constexpr uint32_t kTmemCols = 512;  // group g at columns [64 g, 64 g + 64)
+constexpr uint32_t kTmemCols = 512;
+
+template <int BN>
+struct OzCfg {
+  static constexpr int B_PLANE_BYTES = BN * OBK;
+  static constexpr int B_STAGE_BYTES = S * B_PLANE_BYTES;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (3 * STAGE_BYTES + 3072 <= 227 * 1024) ? 3 : 2;
+  static constexpr int SET_COLS = (S * BN <= 256) ? 256 : 512;  // TMEM columns per accumulator set
+  static constexpr int NSETS = 512 / SET_COLS;
+  static constexpr int PLANES_PER_MMA = (256 / BN) < S ? (256 / BN) : S;  // N <= 256 per instruction
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 2048 /*barriers + column scales*/;
+  static constexpr int HC = BN / (OEPI_WARPS / 4);  // columns per epilogue thread
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -93,7 +108,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(4) << 61;
   return d;
 }
-// kind::i8: D = S32 (c_format 2), A = B = signed 8 bit (format 1), both K-major, M = 128, N = 64
+// kind::i8: D = S32 (c_format 2), A = B = signed 8 bit (format 1), both K-major, M = 128, N = n
 // (cute::UMMA::InstrDescriptor bit layout)
 __host__ __device__ constexpr uint32_t instr_desc_i8(int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(OBM >> 4) << 24);
@@ -130,8 +145,9 @@ struct OzakiParams {
   int b_tile_rows;      // rows of the B split array between consecutive tiles (== nbp when contiguous)
   const double* scale_a;
   const double* scale_b;
-  int gx, gy;          // tile grid (M / 128, N / 64)
+  int gx, gy;          // tile grid (M / 128, N / BN)
   int tiles_per_cta;
+  const int* guard;    // non-null: return at once when *guard != 0 (the native fp64 kernel takes the step)
 };
 
 // signed 64-bit integer (|v| < 2^51) -> double, exactly, on the integer + fp64-add pipes (no I2F)
@@ -139,9 +155,9 @@ __device__ __forceinline__ double i64_to_f64_exact(long long v) {
   return __longlong_as_double(0x4330000000000000LL + (v + (1LL << 51))) - 0x1.8p52;
 }
 
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, int (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr)
                : "memory");
 }
@@ -149,24 +165,24 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, int (&v)[4]) {
 // Fold + store of one thread's row segment (HC columns) of a finished tile. FULL = the tile lies entirely in the
 // lower triangle (no element mask, branch-free); otherwise `lim` = number of leading columns of the segment that are
 // on or below the diagonal for this row.
-template <bool FULL, int HC>
+template <bool FULL, int HC, int BN>
 __device__ __forceinline__ void ozaki_fold_store(uint32_t taddr, double* Cg, long ldc, const double (&cv)[HC],
                                                  double row_scale, const double* cs, int lim) {
 #pragma unroll
-  for (int c0 = 0; c0 < HC; c0 += 4) {
-    int acc[S][4];
+  for (int c0 = 0; c0 < HC; c0 += 8) {
+    int acc[S][8];
 #pragma unroll
     for (int g = 0; g < S; ++g)
-      tmem_ld4(taddr + static_cast<uint32_t>(g * OBN + c0), acc[g]);
+      tmem_ld8(taddr + static_cast<uint32_t>(g * BN + c0), acc[g]);
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      // sum_g acc_g 128^-g = (hi + lo 2^-28) 2^-21 with two exact 46-bit integers
-      const long long hi = (static_cast<long long>(acc[0][j]) << 21) + (static_cast<long long>(acc[1][j]) << 14) +
-                           (static_cast<long long>(acc[2][j] * 128 + acc[3][j]));
-      const long long lo = (static_cast<long long>(acc[4][j]) << 21) + (static_cast<long long>(acc[5][j]) << 14) +
-                           (static_cast<long long>(acc[6][j] * 128 + acc[7][j]));
-      const double v = fma(i64_to_f64_exact(lo), 0x1p-28, i64_to_f64_exact(hi));
+    for (int j = 0; j < 8; ++j) {
+      // sum_g acc_g 256^-g = (hi + lo 2^-24) 2^-24 with two exact integers (|hi| < 2^48, |lo| < 2^43)
+      const long long hi = (static_cast<long long>(acc[0][j]) << 24) + (static_cast<long long>(acc[1][j]) << 16) +
+                           (static_cast<long long>(acc[2][j]) << 8) + static_cast<long long>(acc[3][j]);
+      const long long lo = (static_cast<long long>(acc[4][j]) << 16) + (static_cast<long long>(acc[5][j]) << 8) +
+                           static_cast<long long>(acc[6][j]);
+      const double v = fma(i64_to_f64_exact(lo), 0x1p-24, i64_to_f64_exact(hi));
       const double o = fma(v, row_scale * cs[c0 + j], cv[c0 + j]);
       if (FULL || c0 + j < lim)
         Cg[static_cast<long>(c0 + j) * ldc] = o;
@@ -174,16 +190,21 @@ __device__ __forceinline__ void ozaki_fold_store(uint32_t taddr, double* Cg, lon
   }
 }
 
+template <int BN>
 __global__ void __launch_bounds__(OTHREADS, 1)
     gemm_ozaki_i8_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mB, const OzakiParams p) {
+  using Cfg = OzCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES, NSETS = Cfg::NSETS;
+  if (p.guard != nullptr && *p.guard != 0)
+    return;  // this step runs on the native fp64 kernel (uniform across the grid)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + OSTAGES * OSTAGE_BYTES);
-  uint64_t* empty = full + OSTAGES;
-  uint64_t* tmem_full = empty + OSTAGES;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
-  double* col_scale = reinterpret_cast<double*>(tiles + OSTAGES * OSTAGE_BYTES + 128);  // 2 x OBN doubles (tile parity)
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;   // [NSETS]
+  uint64_t* tmem_empty = tmem_full + 2;   // [NSETS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  double* col_scale = reinterpret_cast<double*>(tiles + STAGES * Cfg::STAGE_BYTES + 128);  // 2 x BN doubles (tile parity)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned lin = blockIdx.x;
@@ -192,22 +213,19 @@ __global__ void __launch_bounds__(OTHREADS, 1)
     OZ_TRACE(0);
   const int KB = p.K / OBK;
   // This CTA owns the tiles with linear index [first, last) (row tile fastest: consecutive tiles share their B rows).
-  // A bounded number of tiles per CTA keeps the CTAs short-lived, so the high-priority panel kernels of the POTRF
-  // schedule still get SMs as CTAs retire, while set-up, TMEM allocation and the first TMA loads of a tile are
-  // amortised / overlapped with the previous tile's epilogue.
   const int first = blockIdx.x * p.tiles_per_cta;
   const int last = min(first + p.tiles_per_cta, p.gx * p.gy);
-  // Rasterization: row tiles in chunks of kRowChunk (8192 rows = 32 MB of A digit planes, L2 resident), all column
+  // Rasterization: row tiles in chunks of kRowChunk (8192 rows = 29 MB of A digit planes, L2 resident), all column
   // tiles of a chunk before the next chunk, row tile fastest inside a column — so the A planes are read from HBM
-  // once per chunk instead of once per column tile when the panel (132 MB at 32768 rows) exceeds L2.
+  // once per chunk instead of once per column tile when the panel (115 MB at 32768 rows) exceeds L2.
   auto tile_of = [&](int l, int& row0, int& col0, long& grow0, long& gcol0) {
     const int per_chunk = kRowChunk * p.gy;
     const int chunk = l / per_chunk, rem = l - chunk * per_chunk;
     const int rows_here = min(kRowChunk, p.gx - chunk * kRowChunk);
     const int by = rem / rows_here, bx = chunk * kRowChunk + rem - by * rows_here;
     row0 = bx * OBM;
-    col0 = by * OBN;
-    return classify_tile(p.g, row0, col0, OBM, OBN, grow0, gcol0);
+    col0 = by * BN;
+    return classify_tile(p.g, row0, col0, OBM, BN, grow0, gcol0);
   };
   {
     bool any = false;
@@ -221,12 +239,14 @@ __global__ void __launch_bounds__(OTHREADS, 1)
   }
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < OSTAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
-    mbar_init(tmem_empty, OEPI_WARPS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], OEPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mB)) : "memory");
@@ -242,7 +262,7 @@ __global__ void __launch_bounds__(OTHREADS, 1)
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer: runs ahead into the next tile while the epilogue of the current one is busy =====
+      // ===== TMA producer: runs ahead into the next tiles while MMAs / epilogues of the current ones are busy =====
       int it = 0;  // stage uses so far
       for (int l = first; l < last; ++l) {
         int row0, col0;
@@ -251,11 +271,11 @@ __global__ void __launch_bounds__(OTHREADS, 1)
           continue;
         const int brow = p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp;
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % OSTAGES;
-          const uint32_t ph = (it / OSTAGES) & 1;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], OSTAGE_BYTES);
-          uint8_t* st = tiles + s * OSTAGE_BYTES;
+          mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          uint8_t* st = tiles + s * Cfg::STAGE_BYTES;
           tma_load_3d(st, &mA, &full[s], kb * OBK, p.a_row + row0, 0);
           tma_load_3d(st + A_STAGE_BYTES, &mB, &full[s], kb * OBK, brow, 0);
         }
@@ -272,18 +292,20 @@ __global__ void __launch_bounds__(OTHREADS, 1)
         long gr, gc;
         if (tile_of(l, row0, col0, gr, gc) == 0)
           continue;
-        if (tcount > 0) {  // the epilogue must have drained the accumulators of the previous tile
-          mbar_wait(tmem_empty, (tcount - 1) & 1);
+        const int set = tcount % NSETS, use = tcount / NSETS;
+        if (use > 0) {  // the epilogue must have drained this accumulator set (its previous use)
+          mbar_wait(&tmem_empty[set], (use - 1) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        const uint32_t tset = tmem_base + static_cast<uint32_t>(set * Cfg::SET_COLS);
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % OSTAGES;
-          const uint32_t ph = (it / OSTAGES) & 1;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[s], ph);
           if (it == 0)
             OZ_TRACE(2);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t stA = smem_u32(tiles + s * OSTAGE_BYTES);
+          const uint32_t stA = smem_u32(tiles + s * Cfg::STAGE_BYTES);
           const uint32_t stB = stA + A_STAGE_BYTES;
 #pragma unroll
           for (int ks = 0; ks < OBK / 32; ++ks) {
@@ -291,16 +313,15 @@ __global__ void __launch_bounds__(OTHREADS, 1)
 #pragma unroll
             for (int t = 0; t < S; ++t) {
               const uint64_t ad = make_kmajor_sw64_desc(stA + t * A_PLANE_BYTES) + adv;
-              // Digit plane t of A meets planes u = 0 .. 7-t of B; their groups g = t + u sit side by side in TMEM
-              // (64 columns each) and the B planes side by side in shared memory (64 rows each), so ONE instruction
-              // with N = 64 (8 - t) covers them all — split only at the N <= 256 limit of the instruction:
-              // 12 large MMAs per k-step instead of 36 small ones. The first product of every group
-              // (kb = ks = t = 0) overwrites its accumulator.
+              // Digit plane t of A meets planes u = 0 .. 6-t of B; their groups g = t + u sit side by side in TMEM
+              // (BN columns each) and the B planes side by side in shared memory (BN rows each), so ONE instruction
+              // with N = BN (7 - t) covers them all — split only at the N <= 256 limit of the instruction. The first
+              // product of every group (kb = ks = t = 0) overwrites its accumulator.
 #pragma unroll
-              for (int u0 = 0; u0 < S - t; u0 += 4) {
-                const int planes = (S - t - u0) < 4 ? (S - t - u0) : 4;
-                const uint64_t bd = make_kmajor_sw64_desc(stB + u0 * B_PLANE_BYTES) + adv;
-                umma_i8(tmem_base + static_cast<uint32_t>((t + u0) * OBN), ad, bd, instr_desc_i8(planes * OBN), (kb | ks | t) != 0);
+              for (int u0 = 0; u0 < S - t; u0 += Cfg::PLANES_PER_MMA) {
+                const int planes = (S - t - u0) < Cfg::PLANES_PER_MMA ? (S - t - u0) : Cfg::PLANES_PER_MMA;
+                const uint64_t bd = make_kmajor_sw64_desc(stB + u0 * Cfg::B_PLANE_BYTES) + adv;
+                umma_i8(tset + static_cast<uint32_t>((t + u0) * BN), ad, bd, instr_desc_i8(planes * BN), (kb | ks | t) != 0);
               }
             }
           }
@@ -308,7 +329,7 @@ __global__ void __launch_bounds__(OTHREADS, 1)
         }
         if (tcount == 0)
           OZ_TRACE(3);
-        umma_commit(tmem_full);  // accumulators of this tile complete
+        umma_commit(&tmem_full[set]);  // accumulators of this tile complete
         ++tcount;
       }
     }
@@ -318,7 +339,7 @@ __global__ void __launch_bounds__(OTHREADS, 1)
     const int q = warp & 3, part = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row of the tile held by this thread
     const int e = threadIdx.x - 64;  // 0 .. 32 * OEPI_WARPS - 1
-    constexpr int HC = OBN / (OEPI_WARPS / 4);  // columns per thread
+    constexpr int HC = Cfg::HC;
     const int cb = part * HC;
     int tcount = 0;
     for (int l = first; l < last; ++l) {
@@ -327,10 +348,11 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       const int cls = tile_of(l, row0, col0, grow0, gcol0);
       if (cls == 0)
         continue;
-      double* cs = col_scale + (tcount & 1) * OBN;
-      if (e < OBN)
+      const int set = tcount % NSETS, use = tcount / NSETS;
+      double* cs = col_scale + (tcount & 1) * BN;
+      if (e < BN)
         cs[e] = p.scale_b[p.b_row + (col0 / p.nbp) * p.b_tile_rows + col0 % p.nbp + e];
-      const double row_scale = p.scale_a[p.a_row + row0 + r] * p.alpha * 0x1p-35;  // 2^-14 digits, 2^-21 from the fold
+      const double row_scale = p.scale_a[p.a_row + row0 + r] * p.alpha * 0x1p-38;  // 2^-14 digits, 2^-24 from the fold
       double* Cg = p.C + row0 + r + static_cast<long>(col0 + cb) * p.ldc;
       // columns [0, lim) of this thread's segment are on or below the diagonal
       const long room = (grow0 + r) - (gcol0 + cb) + 1;
@@ -342,20 +364,20 @@ __global__ void __launch_bounds__(OTHREADS, 1)
       for (int j = 0; j < HC; ++j)
         cv[j] = (j < lim) ? Cg[static_cast<long>(j) * p.ldc] : 0.0;
       asm volatile("bar.sync 1, %0;" ::"n"(32 * OEPI_WARPS) : "memory");  // column scales of this tile are in place
-      mbar_wait(tmem_full, tcount & 1);
+      mbar_wait(&tmem_full[set], use & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (threadIdx.x == 64 && tcount == 0)
         OZ_TRACE(4);
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cb);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(set * Cfg::SET_COLS + cb);
       // tcgen05.ld is warp-collective (.sync.aligned): the path must be chosen per WARP, never per thread
       if (__all_sync(0xffffffffu, lim == HC))
-        ozaki_fold_store<true, HC>(taddr, Cg, p.ldc, cv, row_scale, cs + cb, lim);
+        ozaki_fold_store<true, HC, BN>(taddr, Cg, p.ldc, cv, row_scale, cs + cb, lim);
       else
-        ozaki_fold_store<false, HC>(taddr, Cg, p.ldc, cv, row_scale, cs + cb, lim);
+        ozaki_fold_store<false, HC, BN>(taddr, Cg, p.ldc, cv, row_scale, cs + cb, lim);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0)
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tmem_empty)) : "memory");
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[set])) : "memory");
       if (threadIdx.x == 64 && tcount == 0)
         OZ_TRACE(5);
       ++tcount;
@@ -370,13 +392,18 @@ __global__ void __launch_bounds__(OTHREADS, 1)
     OZ_TRACE(6);
 }
 
-// x (rows x kdim, column-major with leading dimension ld) -> 8 int8 digit planes (K-major) + 2^e per row.
-// Block = 32 rows x 8 k-groups (256 threads); thread (r, kg) owns k = kg, kg + 8, ... of its row in registers
-// (loads of a warp = 32 consecutive rows of one column: coalesced).
+// x (rows x kdim, column-major with leading dimension ld) -> 7 int8 digit planes (K-major) + 2^e per row.
+// Block = 32 rows x 8 k-groups (256 threads); thread (r, kg) owns k = kg * PER .. of its row in registers (loads of a
+// warp = 32 consecutive rows of one column: coalesced).
+// Digits: |x| 2^-e < 1/2 (e = ilogb(row max) + 2); M = rn(x 2^(55-e)) is a 55-bit signed integer, cut from the LOW end
+// into balanced radix-256 digits d_6 .. d_1 in [-128, 127] (d = ((M + 128) & 255) - 128, M <- (M - d) / 256) and a top
+// digit |d_0| <= 65:   x = 2^e sum_t d_t 2^(-7-8t) + r,  |r| <= 2^(e-56)  (entries within a factor 4 of the row maximum
+// are exact). `flag` (may be null): raised when a nonzero entry is rounded AND keeps fewer than min_bits significant bits.
 template <int KDIM>
 __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict__ x, long ld, int rows,
                                                        signed char* __restrict__ q, long plane_stride,
-                                                       double* __restrict__ scale, int tile_rows, long tile_stride) {
+                                                       double* __restrict__ scale, int tile_rows, long tile_stride,
+                                                       int* __restrict__ flag, int min_bits) {
   constexpr int KG = 8, PER = KDIM / KG;  // k values per thread, contiguous chunk [kg * PER, (kg + 1) * PER)
   __shared__ double smax[KG][33];
   const int tr = threadIdx.x & 31, kg = threadIdx.x >> 5;
@@ -395,7 +422,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict_
 #pragma unroll
   for (int i = 0; i < KG; ++i)
     m = fmax(m, smax[i][tr]);
-  // |v| * 2^-e <= 0.5   (e = ilogb(max) + 2);   all-zero (or non-finite) rows: e = 0
+  // |v| * 2^-e < 0.5   (e = ilogb(max) + 2);   all-zero (or non-finite) rows: e = 0
   int e = 0;
   if (m > 0.0 && m < 1.0e300)
     e = ilogb(m) + 2;
@@ -405,23 +432,32 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict_
   // (the digits themselves cannot carry non-finite values).
   if (kg == 0 && live)
     scale[r] = (m < INFINITY) ? __hiloint2double((1023 + e) << 20, 0) : __longlong_as_double(0x7FF8000000000000LL);
+  long long M[PER];
+  bool starved = false;
+  const long long keep = (min_bits > 0) ? (1LL << (min_bits - 1)) : 0;
 #pragma unroll
-  for (int i = 0; i < PER; ++i)
-    v[i] *= down;
+  for (int i = 0; i < PER; ++i) {
+    const double sv = (m < INFINITY) ? (v[i] * down) * 0x1p55 : 0.0;  // exact scaling (two steps: 2^(55-e) may overflow)
+    M[i] = __double2ll_rn(sv);
+    const long long am = M[i] < 0 ? -M[i] : M[i];
+    starved |= (static_cast<double>(M[i]) != sv) && (am < keep);
+  }
+  if (flag != nullptr && starved && live)
+    atomicOr(flag, 1);
   if (!live)
     return;
   signed char* dst = q + static_cast<long>(r) * KDIM + kg * PER;
 #pragma unroll 1
-  for (int t = 0; t < S; ++t) {
+  for (int t = S - 1; t >= 0; --t) {
     uint32_t w[PER / 4];
 #pragma unroll
     for (int i = 0; i < PER; i += 4) {
       uint32_t pack = 0;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const double s = v[i + b] * 128.0;
-        const int d = __double2int_rn(s);  // |d| <= 64
-        v[i + b] = s - static_cast<double>(d);
+        const long long mm = M[i + b];
+        const int d = (t > 0) ? static_cast<int>((mm + 128) & 255) - 128 : static_cast<int>(mm);
+        M[i + b] = (mm - d) >> 8;
         pack |= (static_cast<uint32_t>(d) & 0xFFu) << (8 * b);
       }
       w[i / 4] = pack;
@@ -448,7 +484,26 @@ EncodeFn encode_fn() {
   return fn;
 }
 
+// C tile width of the int8 kernel: 32 (two TMEM accumulator sets, default) or 64 (one set; DLAF_B200_OZAKI_BN=64)
+int ozaki_bn() {
+  static const int v = [] {
+    const char* e = std::getenv("DLAF_B200_OZAKI_BN");
+    const int b = e ? std::atoi(e) : 32;
+    return b == 64 ? 64 : 32;
+  }();
+  return v;
+}
+
 }  // namespace
+
+int ozaki_min_bits() {
+  static const int v = [] {
+    const char* e = std::getenv("DLAF_B200_OZAKI_MIN_BITS");
+    const int b = e ? std::atoi(e) : 16;
+    return b < 0 ? 0 : (b > 53 ? 53 : b);
+  }();
+  return v;
+}
 
 void OzakiSplit::allocate(long rows_max, int kdim_) {
   release();
@@ -458,13 +513,13 @@ void OzakiSplit::allocate(long rows_max, int kdim_) {
   DLAF_CUDA_CHECK(cudaMalloc(&q, static_cast<size_t>(S) * rows * kdim));
   DLAF_CUDA_CHECK(cudaMalloc(&scale, sizeof(double) * rows));
   DLAF_CUDA_CHECK(cudaMemset(q, 0, static_cast<size_t>(S) * rows * kdim));
-  // 3-D maps: dim0 = k (contiguous, bytes), dim1 = row, dim2 = digit plane; box = 64 k x {128, 64} rows x 8 planes;
+  // 3-D maps: dim0 = k (contiguous, bytes), dim1 = row, dim2 = digit plane; box = 64 k x {128, BN} rows x 7 planes;
   // 64-byte swizzle
   const cuuint64_t dims[3] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(S)};
   const cuuint64_t strides[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(kdim) * static_cast<cuuint64_t>(rows)};
   const cuuint32_t estr[3] = {1, 1, 1};
   for (int i = 0; i < 2; ++i) {
-    const cuuint32_t box[3] = {OBK, static_cast<cuuint32_t>(i == 0 ? OBM : OBN), S};
+    const cuuint32_t box[3] = {OBK, static_cast<cuuint32_t>(i == 0 ? OBM : ozaki_bn()), S};
     CUtensorMap* m = reinterpret_cast<CUtensorMap*>(i == 0 ? map_a : map_b);
     const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, q, dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
@@ -480,18 +535,19 @@ void OzakiSplit::release() {
   scale = nullptr;
 }
 
-void OzakiSplit::split(const double* x, long ld, long nrows, cudaStream_t s, int tile_rows, long tile_stride) {
+void OzakiSplit::split(const double* x, long ld, long nrows, cudaStream_t s, int tile_rows, long tile_stride, int* flag) {
   DLAF_B200_ASSERT(nrows <= rows, "split buffer too small");
   if (nrows <= 0)
     return;
   const unsigned grid = static_cast<unsigned>((nrows + 31) / 32);
   const long plane_stride = rows * static_cast<long>(kdim);
   const int tr = tile_rows > 0 ? tile_rows : 1;
+  const int mb = ozaki_min_bits();
   switch (kdim) {
-    case 128: split_i8_kernel<128><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
-    case 256: split_i8_kernel<256><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
-    case 384: split_i8_kernel<384><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
-    case 512: split_i8_kernel<512><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride); break;
+    case 128: split_i8_kernel<128><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
+    case 256: split_i8_kernel<256><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
+    case 384: split_i8_kernel<384><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
+    case 512: split_i8_kernel<512><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
     default: DLAF_B200_ASSERT(false, "Ozaki split: unsupported k (128, 256, 384 or 512)");
   }
   DLAF_CUDA_CHECK(cudaGetLastError());
@@ -544,18 +600,46 @@ void ozaki_set_clock_trace(long long* dev_buffer) {
 
 static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
 
-void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long a_row, const OzakiSplit& sb, long b_row,
-                          cudaStream_t stream, long b_tile_rows) {
-  if (a.M <= 0 || a.N <= 0)
-    return;
-  DLAF_B200_ASSERT(a.M % OBM == 0 && a.N % OBN == 0 && a.K % OBK == 0 && a.K == sa.kdim && a.K == sb.kdim,
-                   "ozaki gemm shape");
-  DLAF_B200_ASSERT((a.alpha == 1.0 || a.alpha == -1.0) && a.beta == 1.0, "ozaki gemm: C += +-A B^T only");
+namespace {
+template <int BN>
+void launch_ozaki_bn(const OzakiParams& p0, const GemmArgsT<double>& a, const OzakiSplit& sa, const OzakiSplit& sb,
+                     cudaStream_t stream) {
+  using Cfg = OzCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    DLAF_CUDA_CHECK(cudaFuncSetAttribute(gemm_ozaki_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OSMEM_BYTES));
+    DLAF_CUDA_CHECK(cudaFuncSetAttribute(gemm_ozaki_i8_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
     configured = true;
   }
+  OzakiParams p = p0;
+  p.gx = a.M / OBM;
+  p.gy = a.N / BN;
+  // Tiles per CTA: large launches amortise set-up over up to 16 tiles (~60-120 us CTAs), small ones keep every SM
+  // busy. DLAF_B200_OZAKI_TPC overrides.
+  static const int tpc_env = [] {
+    const char* e = std::getenv("DLAF_B200_OZAKI_TPC");
+    return e ? std::atoi(e) : 0;
+  }();
+  const long ntiles = static_cast<long>(p.gx) * p.gy;
+  const long unit = ntiles * BN / 64;  // in round-1 tile units (128 x 64)
+  int tpc = tpc_env;
+  if (tpc <= 0)  // trailing matrix >= 16K: 8 units, >= 8K: 4, >= 4K: 2
+    tpc = (unit >= 32768 ? 8 : (unit >= 8192 ? 4 : (unit >= 2048 ? 2 : 1))) * (64 / BN);
+  p.tiles_per_cta = tpc;
+  const unsigned grid = static_cast<unsigned>((ntiles + tpc - 1) / tpc);
+  gemm_ozaki_i8_kernel<BN><<<grid, OTHREADS, Cfg::SMEM_BYTES, stream>>>(*reinterpret_cast<const CUtensorMap*>(sa.map_a),
+                                                                        *reinterpret_cast<const CUtensorMap*>(sb.map_b), p);
+  DLAF_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long a_row, const OzakiSplit& sb, long b_row,
+                          cudaStream_t stream, long b_tile_rows, const int* guard) {
+  if (a.M <= 0 || a.N <= 0)
+    return;
+  DLAF_B200_ASSERT(a.M % OBM == 0 && a.N % 64 == 0 && a.K % OBK == 0 && a.K == sa.kdim && a.K == sb.kdim && a.K <= 512,
+                   "ozaki gemm shape");
+  DLAF_B200_ASSERT((a.alpha == 1.0 || a.alpha == -1.0) && a.beta == 1.0, "ozaki gemm: C += +-A B^T only");
   OzakiParams p;
   p.C = a.C;
   p.ldc = a.ldc;
@@ -568,24 +652,13 @@ void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long
   p.b_tile_rows = static_cast<int>(b_tile_rows > 0 ? b_tile_rows : a.nbp);
   p.scale_a = sa.scale;
   p.scale_b = sb.scale;
-  p.gx = a.M / OBM;
-  p.gy = a.N / OBN;
-  // Tiles per CTA: large launches amortise set-up over up to 8 tiles (~100 us CTAs), small ones keep every SM busy
-  // (measured in the full POTRF, profiles/r01_ozaki_tpc_sweep.log). DLAF_B200_OZAKI_TPC overrides.
-  static const int tpc_env = [] {
-    const char* e = std::getenv("DLAF_B200_OZAKI_TPC");
-    return e ? std::atoi(e) : 0;
-  }();
-  const long grid_tiles = static_cast<long>(p.gx) * p.gy;
-  int tpc = tpc_env;
-  if (tpc <= 0)  // trailing matrix >= 16K: 8, >= 8K: 4, >= 4K: 2
-    tpc = grid_tiles >= 32768 ? 8 : (grid_tiles >= 8192 ? 4 : (grid_tiles >= 2048 ? 2 : 1));
-  p.tiles_per_cta = tpc;
-  const long ntiles = static_cast<long>(p.gx) * p.gy;
-  const unsigned grid = static_cast<unsigned>((ntiles + tpc - 1) / tpc);
-  gemm_ozaki_i8_kernel<<<grid, OTHREADS, OSMEM_BYTES, stream>>>(*reinterpret_cast<const CUtensorMap*>(sa.map_a),
-                                                                 *reinterpret_cast<const CUtensorMap*>(sb.map_b), p);
-  DLAF_CUDA_CHECK(cudaGetLastError());
+  p.gx = p.gy = 0;
+  p.tiles_per_cta = 1;
+  p.guard = guard;
+  if (ozaki_bn() == 64)
+    launch_ozaki_bn<64>(p, a, sa, sb, stream);
+  else
+    launch_ozaki_bn<32>(p, a, sa, sb, stream);
 }
 
 }  // namespace dlaf_b200

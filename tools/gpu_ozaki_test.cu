@@ -63,7 +63,7 @@ int main() {
       sb.split(dB, ldb, rowsB, 0);
       DLAF_CUDA_CHECK(cudaDeviceSynchronize());
       if (data != 0 || kdim == 512) {
-        // slicing exactness: x == 2^e sum_t q_t 128^-(t+1) up to 2^(e-57)
+        // slicing: x == 2^e sum_t d_t 2^(-7-8t) up to 2^(e-56)
         std::vector<signed char> q((size_t)kOzakiSlices * rowsA * K);
         std::vector<double> sc(rowsA);
         cudaMemcpy(q.data(), sa.q, q.size(), cudaMemcpyDeviceToHost);
@@ -72,17 +72,17 @@ int main() {
         int digit_max = 0;
         for (int r = 0; r < rowsA; ++r)
           for (int k = 0; k < K; ++k) {
-            long double v = 0, w = 1;
+            long double v = 0, w = 2;
             for (int t = 0; t < kOzakiSlices; ++t) {
-              w /= 128;
+              w /= 256;  // 2^(-7-8t)
               const int d = q[(size_t)t * rowsA * K + (size_t)r * K + k];
               digit_max = std::max(digit_max, std::abs(d));
               v += w * d;
             }
             worst = std::fmax(worst, (double)(fabsl(v * sc[r] - A[r + k * lda]) / sc[r]));
           }
-        std::printf("split k=%d data %d: max |x - digits| / 2^e = %.3e (bound 2^-57 = %.3e), max |digit| %d\n", kdim, data,
-                    worst, std::ldexp(1.0, -57), digit_max);
+        std::printf("split k=%d data %d: max |x - digits| / 2^e = %.3e (bound 2^-56 = %.3e), max |digit| %d\n", kdim, data,
+                    worst, std::ldexp(1.0, -56), digit_max);
       }
       // reference in long double: C + alpha * A[128:,:] * B[64:,:]^T
       std::vector<long double> ref((size_t)M * N);
@@ -129,6 +129,42 @@ int main() {
       sa.release(); sb.release();
       cudaFree(dA); cudaFree(dB); cudaFree(dC);
     }
+  }
+
+  // ---- guard: flag raised only for rows spanning too many binades; guarded kernels are mutually exclusive
+  {
+    const int n = 256, K = 512;
+    std::vector<double> X((size_t)n * K);
+    double* dX; int* dflag; double* dC;
+    cudaMalloc(&dX, X.size() * 8); cudaMalloc(&dflag, 8); cudaMalloc(&dC, (size_t)n * n * 8);
+    OzakiSplit sp; sp.allocate(n, K);
+    for (int variant = 0; variant < 4; ++variant) {
+      for (auto& x : X) x = dist(rng);
+      if (variant == 1) X[17 + 33 * n] = std::ldexp(X[17 + 33 * n], -45);   // one entry 2^-45 below its row: rounded, < 16 bits kept
+      if (variant == 2) X[17 + 33 * n] = std::ldexp(1.0, -50);               // tiny but EXACT (a power of two): no loss, no flag
+      if (variant == 3) X[5 + 7 * n] = 0.0;                                  // zeros never raise the flag
+      cudaMemcpy(dX, X.data(), X.size() * 8, cudaMemcpyHostToDevice);
+      cudaMemset(dflag, 0, 8);
+      sp.split(dX, n, n, 0, 0, 0, dflag);
+      std::vector<double> C0((size_t)n * n, 1.0), C1(C0.size());
+      cudaMemcpy(dC, C0.data(), C0.size() * 8, cudaMemcpyHostToDevice);
+      GemmArgs g{};
+      g.A = dX; g.lda = n; g.B = dX; g.ldb = n; g.C = dC; g.ldc = n; g.M = n; g.N = n; g.K = K; g.alpha = -1.0; g.beta = 1.0;
+      g.mask = kMaskLower; g.nbp = 128; g.P = g.Q = 1;
+      launch_gemm_ozaki_i8(g, sp, 0, sp, 0, 0, 0, dflag);
+      DLAF_CUDA_CHECK(cudaDeviceSynchronize());
+      cudaMemcpy(C1.data(), dC, C1.size() * 8, cudaMemcpyDeviceToHost);
+      const bool oz_ran = C1[n - 1] != 1.0;
+      launch_gemm_nt_f64_if(g, dflag, 0);
+      DLAF_CUDA_CHECK(cudaDeviceSynchronize());
+      std::vector<double> C2(C0.size());
+      cudaMemcpy(C2.data(), dC, C2.size() * 8, cudaMemcpyDeviceToHost);
+      const bool native_ran = C2[n - 1] != C1[n - 1];
+      int hf = -1; cudaMemcpy(&hf, dflag, 4, cudaMemcpyDeviceToHost);
+      std::printf("guard variant %d: flag %d, int8 kernel ran %d, native kernel ran %d  (expect %s)\n", variant, hf, (int)oz_ran,
+                  (int)native_ran, variant == 1 ? "1 0 1" : "0 1 0");
+    }
+    sp.release(); cudaFree(dX); cudaFree(dflag); cudaFree(dC);
   }
 
   // ---- phase clocks of one launch (4096 x 4096 full update: 2048 tiles)
@@ -204,7 +240,7 @@ int main() {
           if (err != cudaSuccess) { std::printf("timing FAILED: %s\n", cudaGetErrorString(err)); return 1; }
           const double ms = time_ms(e0, e1) / 3;
           std::printf("%s %dx%dx%d mask %d: %.3f ms  %.2f TFLOP/s (fp64-equivalent%s)\n", variant == 0 ? "ozaki_i8" : "dmma    ",
-                      n, n, K, mask, ms, fl / ms / 1e9, variant == 0 ? "; x36 int8 TOP/s" : "");
+                      n, n, K, mask, ms, fl / ms / 1e9, variant == 0 ? "; x28 int8 TOP/s" : "");
         }
       }
       sp.release();

@@ -241,7 +241,7 @@ EngineSlot<devtype_t<T>>& get_engine(GridCtx& c, const DLAF_descriptor& d, const
       g.pcol = u.vcol;
       g.src_in_col_comm = d.isrc;
       g.src_in_row_comm = d.jsrc;
-      slot.eng.reset(new PotrfEngine<D>(g, cg.row_comm, cg.col_comm));
+      slot.eng.reset(new PotrfEngine<D>(g, cg.row_comm, cg.col_comm, cg.row_comm_h, cg.col_comm_h));
     }
     else {
       // U = (lower factor of the conjugate-transposed problem)^H on the transposed grid: the engine's
@@ -252,7 +252,7 @@ EngineSlot<devtype_t<T>>& get_engine(GridCtx& c, const DLAF_descriptor& d, const
       g.pcol = u.vrow;
       g.src_in_col_comm = d.jsrc;
       g.src_in_row_comm = d.isrc;
-      slot.eng.reset(new PotrfEngine<D>(g, cg.col_comm, cg.row_comm));
+      slot.eng.reset(new PotrfEngine<D>(g, cg.col_comm, cg.row_comm, cg.col_comm_h, cg.row_comm_h));
     }
     slot.key = key;
   }

@@ -52,6 +52,8 @@ CommGrid::CommGrid(Comm* world, int P_, int Q_, char order) : P(P_), Q(Q_) {
   DLAF_NCCL_CHECK(ncclCommSplit(world->nccl, in_grid ? row : NCCL_SPLIT_NOCOLOR, col, &row_comm, nullptr));
   DLAF_NCCL_CHECK(ncclCommSplit(world->nccl, in_grid ? col : NCCL_SPLIT_NOCOLOR, row, &col_comm, nullptr));
   DLAF_NCCL_CHECK(ncclCommSplit(world->nccl, in_grid ? 0 : NCCL_SPLIT_NOCOLOR, world_rank, &grid_comm, nullptr));
+  DLAF_NCCL_CHECK(ncclCommSplit(world->nccl, in_grid ? row : NCCL_SPLIT_NOCOLOR, col, &row_comm_h, nullptr));
+  DLAF_NCCL_CHECK(ncclCommSplit(world->nccl, in_grid ? col : NCCL_SPLIT_NOCOLOR, row, &col_comm_h, nullptr));
 }
 
 CommGrid::~CommGrid() {
@@ -61,6 +63,10 @@ CommGrid::~CommGrid() {
     ncclCommDestroy(col_comm);
   if (grid_comm)
     ncclCommDestroy(grid_comm);
+  if (row_comm_h)
+    ncclCommDestroy(row_comm_h);
+  if (col_comm_h)
+    ncclCommDestroy(col_comm_h);
 }
 
 }  // namespace dlaf_b200

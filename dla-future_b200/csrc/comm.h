@@ -56,6 +56,12 @@ public:
   ncclComm_t row_comm = nullptr;  // ranks of my process row, size Q, my rank = col
   ncclComm_t col_comm = nullptr;  // ranks of my process column, size P, my rank = row
   ncclComm_t grid_comm = nullptr; // all ranks of the grid (info reduction / barriers)
+  // Second, independent pair for the critical-path stream (diagonal tile down the column, first panel tile along the
+  // row): the reference keeps 3 round-robin clones per communicator so that independent collectives do not queue behind
+  // each other (src/communication/communicator_grid.cpp:64-75, include/dlaf/tune.h:162); here one clone per STREAM that
+  // issues collectives is what decouples them (NCCL orders operations per communicator).
+  ncclComm_t row_comm_h = nullptr;
+  ncclComm_t col_comm_h = nullptr;
 };
 
 template <class T>

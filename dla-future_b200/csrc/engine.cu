@@ -42,8 +42,9 @@ inline int cnt_tiles(long g_end, int r, int grid) {
 }  // namespace
 
 template <class T>
-PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclComm_t col_comm)
-    : geo_(g), row_comm_(row_comm), col_comm_(col_comm) {
+PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclComm_t col_comm, ncclComm_t row_comm_h,
+                            ncclComm_t col_comm_h)
+    : geo_(g), row_comm_(row_comm), col_comm_(col_comm), row_comm_h_(row_comm_h), col_comm_h_(col_comm_h) {
   DLAF_B200_ASSERT(g.n >= 0 && g.nb >= 1, "matrix / block size");
   DLAF_B200_ASSERT(g.P >= 1 && g.Q >= 1 && g.prow >= 0 && g.prow < g.P && g.pcol >= 0 && g.pcol < g.Q,
                    "grid coordinates");
@@ -71,6 +72,13 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evD_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evF_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evT1_[i], cudaEventDisableTiming));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evC1_[i], cudaEventDisableTiming));
+  }
+  {
+    // Two chains on P x Q grids: needs the independent communicator pair for the critical-path stream.
+    const char* sc = std::getenv("DLAF_B200_SPLIT_CHAIN");
+    dist_split_ = g.P * g.Q > 1 && (g.P == 1 || col_comm_h != nullptr) && (g.Q == 1 || row_comm_h != nullptr) &&
+                  (sc == nullptr || std::atoi(sc) != 0);
   }
   const size_t wsz = static_cast<size_t>(ns_) * G * G;
   const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
@@ -84,6 +92,8 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
     }
     if (geo_.P * geo_.Q > 1)
       DLAF_CUDA_CHECK(cudaMalloc(&panel_[i], sizeof(T) * tsz * (ltr_ > 0 ? ltr_ : 1)));
+    if (dist_split_ && geo_.Q > 1)
+      DLAF_CUDA_CHECK(cudaMalloc(&crit_[i], sizeof(T) * tsz));
   }
   DLAF_CUDA_CHECK(cudaMalloc(&d_info_, sizeof(int)));
   DLAF_CUDA_CHECK(cudaMallocHost(&h_info_, sizeof(int)));
@@ -130,6 +140,8 @@ PotrfEngine<T>::~PotrfEngine() {
   for (int i = 0; i < 2; ++i) {
     cudaEventDestroy(evF_[i]);
     cudaEventDestroy(evT1_[i]);
+    cudaEventDestroy(evC1_[i]);
+    cudaFree(crit_[i]);
     cudaEventDestroy(evC_[i]);
     cudaEventDestroy(evD_[i]);
     cudaFree(wbuf_[i]);
@@ -560,6 +572,200 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
     download_column(lkc, evP_[slot]);  // block column k is final on this rank
 }
 
+// P_k on a P x Q grid as TWO chains (round 2; round 1 ran everything below on stream H in program order, so that every
+// rank sat inside ncclBroadcast waiting for the owners' potrf + whole-panel TRSM):
+//
+//   stream H (critical):  potrf(k) on its owner | L_kk + inverted blocks down the owner COLUMN (col_comm_h) |
+//                         TRSM of tile (k+1,k) only, on its owner X | that tile along process ROW (k+1) % P (row_comm_h) |
+//                         [factorize(): native update of tile (k+1,k+1) from it on its owner N, potrf(k+1) ...]
+//   stream R (panel):     rest of the panel TRSM | pack | whole local panel along the process rows (row_comm) |
+//                         transposed panel down the process columns (col_comm, grouped) | digit / hi-lo splits | evP(k)
+//
+// The two streams use DIFFERENT communicators (NCCL orders operations per communicator), the reference's answer to the
+// same problem being 3 round-robin communicator clones (src/communication/communicator_grid.cpp:64-75) and per-tile
+// MPI_Ibcast pipelines (communication/broadcast_panel.h:156-187). Collective order per communicator is identical on all
+// of its ranks: one diagonal broadcast and one critical-tile broadcast per step on the H pair, one panel broadcast and one
+// grouped transposed broadcast per step on the R pair.
+template <class T>
+void PotrfEngine<T>::panel_step_dist(int k, bool wait_column) {
+  using NT = NcclType<T>;
+  const int P = geo_.P, Q = geo_.Q;
+  const int owner_r = k % P, owner_c = k % Q;
+  const bool in_row = (geo_.prow == owner_r), in_col = (geo_.pcol == owner_c);
+  const int lkr = k / P, lkc = k / Q;
+  const int li1 = cnt_rows(k + 1), lj1 = cnt_cols(k + 1);
+  const int mt = ltr_ - li1;
+  const size_t tsz = static_cast<size_t>(nbp_) * nbp_;
+  const size_t wsz = static_cast<size_t>(ns_) * G * G;
+  const int slot = k % 2;
+  const bool has_next = k < nt_ - 1;
+  const bool in_next_row = has_next && geo_.prow == (k + 1) % P;  // takes part in the critical-tile broadcast
+  const bool is_x = in_next_row && in_col;                         // owns tile (k+1, k)
+  const bool is_n = in_next_row && geo_.pcol == (k + 1) % Q;       // owns tile (k+1, k+1)
+
+  if (k == 0)
+    chain_stamp(0, 0);
+  chain_stamp(k, 1);
+  // ---------------------------------------------------------------- stream H
+  const T* tkk = nullptr;
+  long ldt = 0;
+  const T* w = nullptr;
+  if (in_col) {
+    wait_columns(lkc + 1, sH_);
+    if (k >= 2)  // diagbuf_[slot] was last read by the panel TRSM of step k-2 (stream R, finished before its evP)
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evP_[slot], 0));
+    if (P > 1) {
+      T* dbuf = diagbuf_[slot];
+      if (in_row) {
+        T* tile = tile_ptr(lkr, lkc);
+        factor_diag_tile(tile, ld_, dbuf + tsz, k, sH_);
+        DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dbuf, sizeof(T) * nbp_, tile, sizeof(T) * ld_, sizeof(T) * nbp_, nbp_,
+                                          cudaMemcpyDeviceToDevice, sH_));
+      }
+      chain_stamp(k, 2);
+      DLAF_NCCL_CHECK(ncclBroadcast(dbuf, dbuf, (tsz + wsz) * NT::mult, NT::value, col_comm_rank(owner_r), col_comm_h_,
+                                    sH_));
+      chain_stamp(k, 3);
+      tkk = dbuf;
+      ldt = nbp_;
+      w = dbuf + tsz;
+    }
+    else {
+      T* tile = tile_ptr(lkr, lkc);
+      factor_diag_tile(tile, ld_, wbuf_[slot], k, sH_);
+      tkk = tile;
+      ldt = ld_;
+      w = wbuf_[slot];
+      chain_stamp(k, 2);
+      chain_stamp(k, 3);
+    }
+    DLAF_CUDA_CHECK(cudaEventRecord(evF_[slot], sH_));
+  }
+  else {
+    chain_stamp(k, 2);
+    chain_stamp(k, 3);
+  }
+  crit_next_ = nullptr;
+  if (is_x) {
+    if (wait_column)  // tile (k+1, k) was updated with panel k-1 on stream M
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sH_, evC1_[(k - 1) % 2], 0));
+    trsm_panel(tile_ptr(li1, lkc), ld_, nbp_, tkk, ldt, w, sH_);
+    DLAF_CUDA_CHECK(cudaEventRecord(evT1_[slot], sH_));
+  }
+  if (in_next_row) {
+    if (Q > 1) {
+      if (is_x)
+        DLAF_CUDA_CHECK(cudaMemcpy2DAsync(crit_[slot], sizeof(T) * nbp_, tile_ptr(li1, lkc), sizeof(T) * ld_,
+                                          sizeof(T) * nbp_, nbp_, cudaMemcpyDeviceToDevice, sH_));
+      DLAF_NCCL_CHECK(ncclBroadcast(crit_[slot], crit_[slot], tsz * NT::mult, NT::value, row_comm_rank(owner_c),
+                                    row_comm_h_, sH_));
+      if (is_n) {
+        crit_next_ = crit_[slot];
+        crit_next_ld_ = nbp_;
+      }
+    }
+    else if (is_n) {  // Q == 1: X and N are the same rank, the tile is used where it lies
+      crit_next_ = tile_ptr(li1, lkc);
+      crit_next_ld_ = ld_;
+    }
+  }
+  chain_stamp(k, 4);
+  // ---------------------------------------------------------------- stream R
+  if (in_col) {
+    wait_columns(lkc + 1, sR_);
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evF_[slot], 0));
+    if (wait_column)  // rows of block column k below the diagonal tile: updated on stream M
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evC_[(k - 1) % 2], 0));
+    const int first = li1 + (is_x ? 1 : 0);
+    if (ltr_ - first > 0)
+      trsm_panel(tile_ptr(first, lkc), ld_, (ltr_ - first) * nbp_, tkk, ldt, w, sR_);
+    if (is_x)
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evT1_[slot], 0));
+  }
+  if (has_next) {
+    if (k >= 2) {  // the panel workspaces / splits of this slot were last read by the updates of step k-2
+      wait_bulk(k - 2, -1, sR_);
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evC_[slot], 0));
+    }
+    if (mt > 0) {
+      if (in_col) {
+        launch_pack_panel<T>(tile_ptr(li1, lkc), ld_, panel_[slot], nbp_, mt, sR_);
+        ++launches_;
+      }
+      if (Q > 1)
+        DLAF_NCCL_CHECK(ncclBroadcast(panel_[slot], panel_[slot], tsz * mt * NT::mult, NT::value,
+                                      row_comm_rank(owner_c), row_comm_, sR_));
+    }
+    if (P > 1 && ltc_ - lj1 > 0) {
+      DLAF_NCCL_CHECK(ncclGroupStart());
+      for (int lj = lj1; lj < ltc_; ++lj) {
+        const long gj = static_cast<long>(lj) * Q + geo_.pcol;
+        const int root_v = static_cast<int>(gj % P);
+        T* recv = panelT_[slot] + tsz * (lj - lj1);
+        const T* send = recv;
+        if (root_v == geo_.prow)
+          send = panel_[slot] + tsz * (gj / P - li1);
+        DLAF_NCCL_CHECK(ncclBroadcast(send, recv, tsz * NT::mult, NT::value, col_comm_rank(root_v), col_comm_, sR_));
+      }
+      DLAF_NCCL_CHECK(ncclGroupEnd());
+    }
+    if constexpr (std::is_same_v<T, float>) {
+      if (use_tf32_) {
+        if (mt > 0) {
+          split_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sR_, nbp_, static_cast<long>(tsz));
+          ++launches_;
+        }
+        if (P > 1 && ltc_ - lj1 > 0) {
+          splitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sR_, nbp_, static_cast<long>(tsz));
+          ++launches_;
+        }
+      }
+    }
+    if constexpr (std::is_same_v<T, double>) {
+      if (use_ozaki_) {
+        if (mt > 0) {
+          osplit_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sR_, nbp_, static_cast<long>(tsz),
+                              oz_flag_ + k);
+          ++launches_;
+        }
+        if (P > 1 && ltc_ - lj1 > 0) {
+          osplitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sR_, nbp_,
+                               static_cast<long>(tsz), oz_flag_ + k);
+          ++launches_;
+        }
+      }
+    }
+  }
+  chain_stamp(k, 5);
+  DLAF_CUDA_CHECK(cudaEventRecord(evP_[slot], sR_));
+  if (in_col)
+    download_column(lkc, evP_[slot]);  // block column k is final on this rank
+}
+
+// Tile (k+1, k+1) -= L(k+1,k) L(k+1,k)^H on its owner, in native arithmetic straight from the critical tile (two-chain
+// schedule on grids): all the next potrf waits for.
+template <class T>
+void PotrfEngine<T>::update_next_diag_from_crit(int k, cudaStream_t st) {
+  if (crit_next_ == nullptr)
+    return;
+  const int li = (k + 1) / geo_.P, lj = (k + 1) / geo_.Q;
+  wait_columns(lj + 1, st);
+  GemmArgsT<T> a{};
+  a.A = crit_next_;
+  a.lda = crit_next_ld_;
+  a.B = crit_next_;
+  a.ldb = crit_next_ld_;
+  a.C = tile_ptr(li, lj);
+  a.ldc = ld_;
+  a.M = a.N = a.K = nbp_;
+  a.alpha = -1.0;
+  a.beta = 1.0;
+  a.mask = kMaskLower;  // relative to the diagonal of this tile
+  a.nbp = 1 << 30;
+  a.P = a.Q = 1;
+  gemm(a, st);
+}
+
 // U_k on my local block columns [cj0, cj0 + ncols), rows from local tile row ri0 on (mrows elements):
 // ONE masked GEMM launch.
 template <class T>
@@ -697,9 +903,23 @@ void PotrfEngine<T>::update(int k, UpdatePart part, cudaStream_t st) {
         return;
       mrows = nbp_;
     }
-    else if (own_diag) {
-      ri0 += 1;
-      mrows -= nbp_;
+    else {
+      if (own_diag) {
+        ri0 += 1;
+        mrows -= nbp_;
+      }
+      // ri0 is now the first local row with global index >= k+2; it IS row k+2 (the tile the next critical TRSM
+      // needs) iff this rank's process row owns it
+      const bool own_first = (k + 2 < nt_) && ((k + 2) % P == geo_.prow);
+      if (part == kNextColumnFirst) {
+        if (!own_first)
+          return;
+        mrows = nbp_;
+      }
+      else if (part == kNextColumnTail && own_first) {
+        ri0 += 1;
+        mrows -= nbp_;
+      }
     }
   }
   if (mrows <= 0)
@@ -914,7 +1134,10 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   for (int c = 1; c < nc; ++c)
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sLc_[c], ev_start_, 0));
 
-  panel_step(0, false);
+  if (dist_split_)
+    panel_step_dist(0, false);
+  else
+    panel_step(0, false);
   for (int k = 0; k < nt_ - 1; ++k) {
     // bulk of U_k on the low-priority stream(s), one launch per column chunk
     const int lj1 = cnt_cols(k + 1);
@@ -958,14 +1181,27 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, evP_[k % 2], 0));
     if (k >= 1)
       wait_bulk(k - 1, own_next ? lj1 : -1, sM_);
-    update(k, kNextColumnRest, sM_);
+    if (dist_split_) {
+      update(k, kNextColumnFirst, sM_);  // tile (k+2, k+1): all the next critical-tile TRSM waits for
+      DLAF_CUDA_CHECK(cudaEventRecord(evC1_[k % 2], sM_));
+      update(k, kNextColumnTail, sM_);
+    }
+    else {
+      update(k, kNextColumnRest, sM_);
+    }
     DLAF_CUDA_CHECK(cudaEventRecord(evC_[k % 2], sM_));
     // critical path on stream H: the diagonal tile (k+1,k+1), then P_{k+1} (its TRSM waits for stream M)
     chain_stamp(k + 1, 0);
     if (k >= 1)
       wait_bulk(k - 1, own_next ? lj1 : -1, sH_);
-    update(k, kNextDiag, sH_);
-    panel_step(k + 1, true);
+    if (dist_split_) {
+      update_next_diag_from_crit(k, sH_);
+      panel_step_dist(k + 1, true);
+    }
+    else {
+      update(k, kNextDiag, sH_);
+      panel_step(k + 1, true);
+    }
   }
   if (host_) {
     DLAF_CUDA_CHECK(cudaEventRecord(evOut_, sOut_));

@@ -48,7 +48,10 @@ class PotrfEngine {
 public:
   static constexpr int G = Gran<T>::value;
 
-  PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclComm_t col_comm);
+  // row_comm_h / col_comm_h: independent clones for the collectives of the critical-path stream (may be null: the
+  // distributed two-chain schedule is then off and every collective runs on stream H like in round 1)
+  PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclComm_t col_comm, ncclComm_t row_comm_h = nullptr,
+              ncclComm_t col_comm_h = nullptr);
   ~PotrfEngine();
   PotrfEngine(const PotrfEngine&) = delete;
   PotrfEngine& operator=(const PotrfEngine&) = delete;
@@ -113,7 +116,9 @@ public:
 
 private:
   void panel_step(int k, bool wait_column);
-  enum UpdatePart { kBulk = 0, kNextDiag = 1, kNextColumnRest = 2 };
+  void panel_step_dist(int k, bool wait_column);  // P x Q > 1, two chains (engine.cu)
+  void update_next_diag_from_crit(int k, cudaStream_t st);
+  enum UpdatePart { kBulk = 0, kNextDiag = 1, kNextColumnRest = 2, kNextColumnFirst = 3, kNextColumnTail = 4 };
   void update(int k, UpdatePart part, cudaStream_t st);
   void launch_update(int k, int cj0, int ncols, int ri0, int mrows, bool count_flops, cudaStream_t st,
                      bool native = false);
@@ -128,6 +133,13 @@ private:
 
   EngineGeometry geo_;
   ncclComm_t row_comm_, col_comm_;
+  ncclComm_t row_comm_h_ = nullptr, col_comm_h_ = nullptr;
+  // distributed two-chain schedule (DLAF_B200_SPLIT_CHAIN, default on when the clones exist)
+  bool dist_split_ = false;
+  T* crit_[2] = {nullptr, nullptr};      // tile (k+1, k) after its TRSM, broadcast along process row (k+1) % P
+  const T* crit_next_ = nullptr;         // operand of the next diagonal-tile update on this rank (null: not the owner)
+  long crit_next_ld_ = 0;
+  cudaEvent_t evC1_[2] = {nullptr, nullptr};  // tile (k+2, k+1) updated with panel k (stream M)
   int nbp_, nt_, ltr_, ltc_, ns_;
   long ld_ = 0;
   T* data_ = nullptr;      // active storage (own slab or external)

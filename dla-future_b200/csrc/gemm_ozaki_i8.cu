@@ -8,15 +8,16 @@
 // product at the int8 tensor rate.
 //
 // Operands: OzakiSplit (split_i8_kernel below): 7 balanced radix-256 digit planes per panel (int8, K-major) + one
-// power-of-two scale per row. Round 2 layout (round 1: 8 radix-128 digits, 36 pairs, 128 x 64 tiles, TMEM full):
-//   * CTA tile 128 x BN of C, BN = 32: the 7 anti-diagonal group accumulators take 7 x 32 = 224 TMEM columns, so TWO
-//     accumulator sets fit the 512 columns and the epilogue of tile i overlaps the MMAs of tile i + 1
-//     (BN = 64: one set, the round-1 structure, kept as an A/B variant: DLAF_B200_OZAKI_BN=64);
+// power-of-two scale per row. Round 2 layout (round 1: 8 radix-128 digits, 36 pairs):
+//   * CTA tile 128 x BN of C. BN = 64 (default): the 7 anti-diagonal group accumulators take 7 x 64 = 448 of the 512 TMEM
+//     columns. BN = 32 (DLAF_B200_OZAKI_BN=32): 224 columns, TWO accumulator sets, the epilogue of tile i overlaps the
+//     MMAs of tile i + 1 — measured slower, because the MMA phase is bound by shared-memory operand reads (~98 B/clk)
+//     and narrow tiles re-read the A planes twice as often per MAC (see ozaki_bn() below);
 //   * digit plane t of A meets planes u = 0 .. 6-t of B, whose accumulators are adjacent in TMEM and whose smem
-//     planes are adjacent rows -> ONE tcgen05.mma.kind::i8 with N = BN (7 - t) <= 256 per plane t: 7 MMAs per k-step;
+//     planes are adjacent rows -> ONE tcgen05.mma.kind::i8 with N = BN (7 - t), split at the N <= 256 limit: 10 (BN = 64) or 7 (BN = 32) MMAs per k-step;
 //   * 18 warps: warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane), warps 2..17 =
 //     epilogue (TMEM lane quadrant = warp % 4, BN / 4 columns each);
-//   * 3 stages x {7 A planes (128 rows x 64 k), 7 B planes (BN rows x 64 k)} = 70 KB per stage, two 3-D TMA boxes
+//   * 2 (BN = 64: 84 KB per stage) or 3 (BN = 32: 70 KB) stages x {7 A planes (128 rows x 64 k), 7 B planes (BN rows x 64 k)}, two 3-D TMA boxes
 //     (k, row, plane) per stage in SWIZZLE_64B K-major UMMA layout; full/empty mbarriers per stage, tmem_full /
 //     tmem_empty per accumulator set; every mbarrier wait is bounded (trap instead of hang);
 //   * a CTA handles a few consecutive tiles (DLAF_B200_OZAKI_TPC) so that it stays short-lived next to the
@@ -484,12 +485,16 @@ EncodeFn encode_fn() {
   return fn;
 }
 
-// C tile width of the int8 kernel: 32 (two TMEM accumulator sets, default) or 64 (one set; DLAF_B200_OZAKI_BN=64)
+// C tile width of the int8 kernel: 64 (one TMEM accumulator set, default) or 32 (two sets: the epilogue overlaps the next
+// tile's MMAs; DLAF_B200_OZAKI_BN=32). Measured (profiles/r02_ozaki_i8_v5_*.log): the MMA phase of BOTH variants runs at
+// ~98 B/clk of shared-memory operand reads, not at the tensor pipe's rate — 128 x 32 tiles read 56 KB per k-step
+// (585 clk instead of 448), 128 x 64 tiles 96 KB (986 clk instead of 896) — so the wider tile wins (93 vs 85 TFLOP/s
+// fp64-equivalent) although its epilogue is exposed.
 int ozaki_bn() {
   static const int v = [] {
     const char* e = std::getenv("DLAF_B200_OZAKI_BN");
-    const int b = e ? std::atoi(e) : 32;
-    return b == 64 ? 64 : 32;
+    const int b = e ? std::atoi(e) : 64;
+    return b == 32 ? 32 : 64;
   }();
   return v;
 }

@@ -7,12 +7,12 @@ CSRC      := dla-future_b200/csrc
 LIBDIR    := dla-future_b200/lib
 LIB       := $(LIBDIR)/libdlaf_b200.so
 
-CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/gemm_zdmma.o build/gemm_tf32_tcgen05.o build/gemm_ozaki_i8.o build/potrf_tile.o build/layout.o build/engine.o build/sm_partition.o build/peak.o build/engine_check.o
+CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/gemm_zdmma.o build/gemm_tf32_tcgen05.o build/gemm_ozaki_i8.o build/potrf_tile.o build/potrf_tile_cluster.o build/layout.o build/engine.o build/sm_partition.o build/peak.o build/engine_check.o
 CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
 OBJS     := $(CU_OBJS) $(CPP_OBJS)
 HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h)
 
-all: $(LIB) tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref miniapp/miniapp_cholesky
+all: $(LIB) tools/gpu_diag_tile_test tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref miniapp/miniapp_cholesky
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -28,8 +28,11 @@ $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lnccl -lpthread
 
-tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_tile.o build/gemm_tf32_tcgen05.o $(HDRS)
-	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/potrf_tile.o build/gemm_tf32_tcgen05.o -lcublas -o $@
+tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_tile.o build/potrf_tile_cluster.o build/gemm_tf32_tcgen05.o $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/potrf_tile.o build/potrf_tile_cluster.o build/gemm_tf32_tcgen05.o -lcublas -o $@
+
+tools/gpu_diag_tile_test: tools/gpu_diag_tile_test.cu build/potrf_tile_cluster.o $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $< build/potrf_tile_cluster.o -o $@
 
 tools/gpu_chain_test: tools/gpu_chain_test.cu build/gemm_dmma.o $(HDRS)
 	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o -o $@
@@ -46,6 +49,6 @@ miniapp/miniapp_cholesky: miniapp/miniapp_cholesky.cpp $(LIB) $(wildcard include
 	g++ $(CXXFLAGS) $< -o $@ -L$(LIBDIR) -ldlaf_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread
 
 clean:
-	rm -rf build tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref $(LIBDIR)/*.so
+	rm -rf build tools/gpu_diag_tile_test tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref $(LIBDIR)/*.so
 
 .PHONY: all clean

@@ -73,6 +73,7 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evF_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evT1_[i], cudaEventDisableTiming));
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evC1_[i], cudaEventDisableTiming));
+    DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&evPc_[i], cudaEventDisableTiming));
   }
   {
     // Two chains on P x Q grids: needs the independent communicator pair for the critical-path stream.
@@ -141,6 +142,7 @@ PotrfEngine<T>::~PotrfEngine() {
     cudaEventDestroy(evF_[i]);
     cudaEventDestroy(evT1_[i]);
     cudaEventDestroy(evC1_[i]);
+    cudaEventDestroy(evPc_[i]);
     cudaFree(crit_[i]);
     cudaEventDestroy(evC_[i]);
     cudaEventDestroy(evD_[i]);
@@ -287,6 +289,26 @@ void PotrfEngine<T>::gemm(const GemmArgsT<T>& a, cudaStream_t st) {
 // two dependent launches per block either way, 349 vs 342 us per tile in isolation, profiles/r01_chain_*.)
 template <class T>
 void PotrfEngine<T>::factor_diag_tile(T* tile, long ld, T* w, int k, cudaStream_t st) {
+  if constexpr (std::is_same_v<T, double>) {
+    // fp64, tiles up to 512: the whole tile (factor + inverted 128-blocks) in ONE cluster launch (potrf_tile_cluster.cu)
+    if (potrf_tile_cluster_supported(nbp_)) {
+      if (profiling_) {
+        while (diag_ev_.size() < diag_used_ + 2) {
+          cudaEvent_t e;
+          DLAF_CUDA_CHECK(cudaEventCreate(&e));
+          diag_ev_.push_back(e);
+        }
+        DLAF_CUDA_CHECK(cudaEventRecord(diag_ev_[diag_used_], st));
+      }
+      launch_potrf_tile_cluster_f64(tile, ld, w, nbp_, d_info_, k * geo_.nb, st);
+      ++launches_;
+      if (profiling_) {
+        DLAF_CUDA_CHECK(cudaEventRecord(diag_ev_[diag_used_ + 1], st));
+        diag_used_ += 2;
+      }
+      return;
+    }
+  }
   for (int j = 0; j < ns_; ++j) {
     T* tjj = tile + static_cast<long>(j) * G * (1 + ld);
     T* wj = w + static_cast<long>(j) * G * G;
@@ -696,9 +718,14 @@ void PotrfEngine<T>::panel_step_dist(int k, bool wait_column) {
         DLAF_NCCL_CHECK(ncclBroadcast(panel_[slot], panel_[slot], tsz * mt * NT::mult, NT::value,
                                       row_comm_rank(owner_c), row_comm_, sR_));
     }
-    if (P > 1 && ltc_ - lj1 > 0) {
-      DLAF_NCCL_CHECK(ncclGroupStart());
-      for (int lj = lj1; lj < ltc_; ++lj) {
+    // Transposed panel: the tile of block column k+1 goes FIRST on the ranks that own that column (it is all the update
+    // of column k+1 on stream M needs besides the row panel), the rest follows in one group.
+    const bool own_next_col = (geo_.pcol == (k + 1) % Q);
+    const int nT = ltc_ - lj1;  // transposed tiles I hold (local columns >= k+1)
+    auto bcast_T = [&](int lj_begin, int lj_end) {
+      if (lj_end - lj_begin > 1)
+        DLAF_NCCL_CHECK(ncclGroupStart());
+      for (int lj = lj_begin; lj < lj_end; ++lj) {
         const long gj = static_cast<long>(lj) * Q + geo_.pcol;
         const int root_v = static_cast<int>(gj % P);
         T* recv = panelT_[slot] + tsz * (lj - lj1);
@@ -707,20 +734,12 @@ void PotrfEngine<T>::panel_step_dist(int k, bool wait_column) {
           send = panel_[slot] + tsz * (gj / P - li1);
         DLAF_NCCL_CHECK(ncclBroadcast(send, recv, tsz * NT::mult, NT::value, col_comm_rank(root_v), col_comm_, sR_));
       }
-      DLAF_NCCL_CHECK(ncclGroupEnd());
-    }
-    if constexpr (std::is_same_v<T, float>) {
-      if (use_tf32_) {
-        if (mt > 0) {
-          split_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sR_, nbp_, static_cast<long>(tsz));
-          ++launches_;
-        }
-        if (P > 1 && ltc_ - lj1 > 0) {
-          splitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sR_, nbp_, static_cast<long>(tsz));
-          ++launches_;
-        }
-      }
-    }
+      if (lj_end - lj_begin > 1)
+        DLAF_NCCL_CHECK(ncclGroupEnd());
+    };
+    const bool early = (P > 1 && own_next_col && nT > 0);
+    if (early)
+      bcast_T(lj1, lj1 + 1);
     if constexpr (std::is_same_v<T, double>) {
       if (use_ozaki_) {
         if (mt > 0) {
@@ -728,13 +747,38 @@ void PotrfEngine<T>::panel_step_dist(int k, bool wait_column) {
                               oz_flag_ + k);
           ++launches_;
         }
-        if (P > 1 && ltc_ - lj1 > 0) {
-          osplitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(ltc_ - lj1) * nbp_, sR_, nbp_,
-                               static_cast<long>(tsz), oz_flag_ + k);
+        if (early) {
+          osplitT_[slot].split(panelT_[slot], nbp_, nbp_, sR_, nbp_, static_cast<long>(tsz), oz_flag_ + k);
           ++launches_;
         }
       }
     }
+    DLAF_CUDA_CHECK(cudaEventRecord(evPc_[slot], sR_));  // (fp32 / complex: the early tile is there, splits follow below)
+    if (P > 1 && nT - (early ? 1 : 0) > 0)
+      bcast_T(lj1 + (early ? 1 : 0), ltc_);
+    if constexpr (std::is_same_v<T, float>) {
+      if (use_tf32_) {
+        if (mt > 0) {
+          split_[slot].split(panel_[slot], nbp_, static_cast<long>(mt) * nbp_, sR_, nbp_, static_cast<long>(tsz));
+          ++launches_;
+        }
+        if (P > 1 && nT > 0) {
+          splitT_[slot].split(panelT_[slot], nbp_, static_cast<long>(nT) * nbp_, sR_, nbp_, static_cast<long>(tsz));
+          ++launches_;
+        }
+      }
+    }
+    if constexpr (std::is_same_v<T, double>) {
+      if (use_ozaki_ && P > 1 && nT - (early ? 1 : 0) > 0) {
+        const int t0 = early ? 1 : 0;
+        osplitT_[slot].split(panelT_[slot] + tsz * t0, nbp_, static_cast<long>(nT - t0) * nbp_, sR_, nbp_,
+                             static_cast<long>(tsz), oz_flag_ + k, static_cast<long>(t0) * nbp_);
+        ++launches_;
+      }
+    }
+  }
+  else {
+    DLAF_CUDA_CHECK(cudaEventRecord(evPc_[slot], sR_));
   }
   chain_stamp(k, 5);
   DLAF_CUDA_CHECK(cudaEventRecord(evP_[slot], sR_));
@@ -1178,7 +1222,7 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
       DLAF_CUDA_CHECK(cudaEventRecord(evBc_[2 * c + k % 2], st));
     }
     // stream M: block column k+1 below its diagonal tile (needs panel k and the bulk of step k-1 there)
-    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, evP_[k % 2], 0));
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, (dist_split_ && use_ozaki_) ? evPc_[k % 2] : evP_[k % 2], 0));
     if (k >= 1)
       wait_bulk(k - 1, own_next ? lj1 : -1, sM_);
     if (dist_split_) {

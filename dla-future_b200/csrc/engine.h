@@ -140,6 +140,7 @@ private:
   const T* crit_next_ = nullptr;         // operand of the next diagonal-tile update on this rank (null: not the owner)
   long crit_next_ld_ = 0;
   cudaEvent_t evC1_[2] = {nullptr, nullptr};  // tile (k+2, k+1) updated with panel k (stream M)
+  cudaEvent_t evPc_[2] = {nullptr, nullptr};  // panel k usable by the update of block column k+1 (stream R, <= evP)
   int nbp_, nt_, ltr_, ltc_, ns_;
   long ld_ = 0;
   T* data_ = nullptr;      // active storage (own slab or external)

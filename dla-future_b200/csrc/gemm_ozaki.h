@@ -43,8 +43,9 @@ struct OzakiSplit {
   // tile_rows / tile_stride describe tile-contiguous panel workspaces: row r of x lives at
   // x + (r / tile_rows) * tile_stride + r % tile_rows (tile_stride == 0: plain column-major).
   // flag (device int, may be null): OR-ed with 1 when the guard criterion above fires for any entry of these rows.
+  // dst_row0: first row of the split buffer to fill (x then points at the source of that row).
   void split(const double* x, long ld, long nrows, cudaStream_t s, int tile_rows = 0, long tile_stride = 0,
-             int* flag = nullptr);
+             int* flag = nullptr, long dst_row0 = 0);
 };
 
 // C = C + alpha * A B^T (alpha = +-1, beta = 1) with A = rows [a_row, a_row + M) of `sa`, B = rows [b_row, b_row + N)

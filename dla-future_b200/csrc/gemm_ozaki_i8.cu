@@ -404,7 +404,7 @@ template <int KDIM>
 __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict__ x, long ld, int rows,
                                                        signed char* __restrict__ q, long plane_stride,
                                                        double* __restrict__ scale, int tile_rows, long tile_stride,
-                                                       int* __restrict__ flag, int min_bits) {
+                                                       int* __restrict__ flag, int min_bits, int dst_row0) {
   constexpr int KG = 8, PER = KDIM / KG;  // k values per thread, contiguous chunk [kg * PER, (kg + 1) * PER)
   __shared__ double smax[KG][33];
   const int tr = threadIdx.x & 31, kg = threadIdx.x >> 5;
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict_
   // A row holding Inf / NaN gets a NaN scale: every C entry it contributes to becomes NaN, like in a native fp64 update
   // (the digits themselves cannot carry non-finite values).
   if (kg == 0 && live)
-    scale[r] = (m < INFINITY) ? __hiloint2double((1023 + e) << 20, 0) : __longlong_as_double(0x7FF8000000000000LL);
+    scale[dst_row0 + r] = (m < INFINITY) ? __hiloint2double((1023 + e) << 20, 0) : __longlong_as_double(0x7FF8000000000000LL);
   long long M[PER];
   bool starved = false;
   const long long keep = (min_bits > 0) ? (1LL << (min_bits - 1)) : 0;
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double* __restrict_
     atomicOr(flag, 1);
   if (!live)
     return;
-  signed char* dst = q + static_cast<long>(r) * KDIM + kg * PER;
+  signed char* dst = q + static_cast<long>(dst_row0 + r) * KDIM + kg * PER;
 #pragma unroll 1
   for (int t = S - 1; t >= 0; --t) {
     uint32_t w[PER / 4];
@@ -540,8 +540,9 @@ void OzakiSplit::release() {
   scale = nullptr;
 }
 
-void OzakiSplit::split(const double* x, long ld, long nrows, cudaStream_t s, int tile_rows, long tile_stride, int* flag) {
-  DLAF_B200_ASSERT(nrows <= rows, "split buffer too small");
+void OzakiSplit::split(const double* x, long ld, long nrows, cudaStream_t s, int tile_rows, long tile_stride, int* flag,
+                       long dst_row0) {
+  DLAF_B200_ASSERT(dst_row0 + nrows <= rows, "split buffer too small");
   if (nrows <= 0)
     return;
   const unsigned grid = static_cast<unsigned>((nrows + 31) / 32);
@@ -549,10 +550,10 @@ void OzakiSplit::split(const double* x, long ld, long nrows, cudaStream_t s, int
   const int tr = tile_rows > 0 ? tile_rows : 1;
   const int mb = ozaki_min_bits();
   switch (kdim) {
-    case 128: split_i8_kernel<128><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
-    case 256: split_i8_kernel<256><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
-    case 384: split_i8_kernel<384><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
-    case 512: split_i8_kernel<512><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb); break;
+    case 128: split_i8_kernel<128><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb, static_cast<int>(dst_row0)); break;
+    case 256: split_i8_kernel<256><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb, static_cast<int>(dst_row0)); break;
+    case 384: split_i8_kernel<384><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb, static_cast<int>(dst_row0)); break;
+    case 512: split_i8_kernel<512><<<grid, 256, 0, s>>>(x, ld, static_cast<int>(nrows), q, plane_stride, scale, tr, tile_stride, flag, mb, static_cast<int>(dst_row0)); break;
     default: DLAF_B200_ASSERT(false, "Ozaki split: unsupported k (128, 256, 384 or 512)");
   }
   DLAF_CUDA_CHECK(cudaGetLastError());

@@ -28,6 +28,14 @@ void launch_potrf128_inv_f64(double* T, long ldt, double* W, long ldw, int* info
 // Measurement aid (tools/): device buffer of 16*8*2 clock64 stamps per launch, nullptr switches it off.
 void potrf_set_clock_trace(long long* dev_buffer);
 
+// Whole diagonal tile in one cluster launch (potrf_tile_cluster.cu): T = nbp x nbp tile (lower triangle in/out), W =
+// nbp / 128 inverted diagonal blocks (each 128 x 128 contiguous, ld 128). nbp in {128, 256, 384, 512}.
+bool potrf_tile_cluster_supported(int nbp);
+void launch_potrf_tile_cluster_f64(double* T, long ldt, double* W, int nbp, int* info, int info_offset,
+                                   cudaStream_t stream);
+// Measurement aid: device buffer of 64 * 4 clock64 stamps (CTA 0, thread 0, per panel step); nullptr = off.
+void potrf_tile_set_clock_trace(long long* dev_buffer);
+
 // Per element type entry point: Cholesky + inverse of one Gran<T> x Gran<T> diagonal block.
 template <class T>
 void launch_potrf_inv(T* t, long ldt, T* w, long ldw, int* info, int info_offset, cudaStream_t stream);

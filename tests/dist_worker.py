@@ -120,7 +120,7 @@ def main():
                             failures.append(("grid residual", n, nb, t, uplo, s, res, gate))
                         if (n, nb, t) == (1000, 128, "d"):
                             bad = loc.copy(order="F")
-                            if (myrow, mycol) == (0, 0):
+                            if (myrow, mycol) == tuple(s):  # the source rank holds global element (0, 0), on the diagonal
                                 bad[0, 0] += 0.5
                             res_bad = pkg.check_cholesky(ctx, uplo, orig, bad, nb, n=n, isrc=s[0], jsrc=s[1])
                             if not res_bad > 1e-6:

@@ -12,7 +12,7 @@ CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
 OBJS     := $(CU_OBJS) $(CPP_OBJS)
 HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h)
 
-all: $(LIB) tools/gpu_diag_tile_test tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref miniapp/miniapp_cholesky
+all: $(LIB) tools/gpu_diag_tile_test tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref tools/cublas_tile_potrf_ref tools/cusolvermg_potrf_ref miniapp/miniapp_cholesky
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -43,6 +43,12 @@ tools/gpu_ozaki_test: tools/gpu_ozaki_test.cu build/gemm_dmma.o build/gemm_ozaki
 # vendor-library GPU reference (measurement aid only; nothing in the product links cuSOLVER)
 tools/cusolver_potrf_ref: tools/cusolver_potrf_ref.cu
 	$(NVCC) $(NVCCFLAGS) $< -lcusolver -lcublas -o $@
+
+tools/cublas_tile_potrf_ref: tools/cublas_tile_potrf_ref.cu
+	$(NVCC) $(NVCCFLAGS) $< -lcusolver -lcublas -o $@
+
+tools/cusolvermg_potrf_ref: tools/cusolvermg_potrf_ref.cu
+	$(NVCC) $(NVCCFLAGS) $< -lcusolverMg -lcusolver -lcublas -o $@
 
 # The driver is plain C++ against include/dlaf (header-only surface) + the C-ABI library.
 miniapp/miniapp_cholesky: miniapp/miniapp_cholesky.cpp $(LIB) $(wildcard include/dlaf/*.h) $(wildcard include/dlaf/*/*.h)

@@ -38,6 +38,8 @@ C_API_SYMBOLS = [
     "dlaf_b200_ozaki_pairs",
     "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops", "dlaf_b200_measure_int8_tensor_peak_tops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
+    "dlaf_b200_rank_global_tile", "dlaf_b200_local_tile_from_global_tile", "dlaf_b200_next_local_tile_from_global_tile",
+    "dlaf_b200_global_tile_from_local_tile",
 ]
 
 
@@ -159,6 +161,13 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_local_rows.restype = ci
     L.dlaf_b200_local_cols.argtypes = [ci, DLAF_descriptor]
     L.dlaf_b200_local_cols.restype = ci
+    cl = ctypes.c_long
+    L.dlaf_b200_rank_global_tile.argtypes = [cl, ci, ci]
+    L.dlaf_b200_rank_global_tile.restype = ci
+    for nm in ("local_tile_from_global_tile", "next_local_tile_from_global_tile", "global_tile_from_local_tile"):
+        f = getattr(L, f"dlaf_b200_{nm}")
+        f.argtypes = [cl, ci, ci, ci]
+        f.restype = cl
     _lib = L
     return L
 

@@ -19,6 +19,7 @@
 
 #include "comm.h"
 #include "common.h"
+#include "distribution.h"
 #include "engine.h"
 #include "util_matrix.h"
 
@@ -172,7 +173,8 @@ GridCtx& grid_from_context(int ctx) {
 }
 
 inline int cnt_tiles(long g_end, int r, int grid) {
-  return g_end > r ? static_cast<int>((g_end - r + grid - 1) / grid) : 0;
+  // tiles of virtual rank r with global index < g_end (distribution.h: next_local_tile_from_global_tile, source 0)
+  return static_cast<int>(next_local_tile_from_global_tile(g_end, grid, r, 0));
 }
 
 struct UserGeom {
@@ -515,10 +517,36 @@ void dlaf_b200_comm_destroy(struct dlaf_b200_comm* comm) noexcept {
   comm_destroy(comm);
 }
 
+#ifdef DLAF_B200_WITH_MPI
+// Real-MPI builds (-DDLAF_B200_WITH_MPI, include/dlaf_c/grid.h): the reference's exact prototype. The NCCL world
+// communicator is bootstrapped over the MPI communicator (the 128-byte unique id travels by MPI_Bcast) once per MPI_Comm.
+static Comm* world_of(MPI_Comm mc) {
+  static std::map<MPI_Comm, Comm*> cache;
+  auto it = cache.find(mc);
+  if (it != cache.end())
+    return it->second;
+  int rank = 0, size = 1;
+  MPI_Comm_rank(mc, &rank);
+  MPI_Comm_size(mc, &size);
+  unsigned char id[DLAF_B200_UNIQUE_ID_BYTES];
+  if (rank == 0)
+    dlaf_b200_get_unique_id(id);
+  MPI_Bcast(id, DLAF_B200_UNIQUE_ID_BYTES, MPI_BYTE, 0, mc);
+  ensure_device();
+  Comm* c = size > 1 ? comm_create(id, rank, size) : nullptr;
+  cache[mc] = c;
+  return c;
+}
+#else
+static Comm* world_of(DLAF_Comm c) {
+  return c;
+}
+#endif
+
 int dlaf_create_grid(DLAF_Comm comm, int nprow, int npcol, char order) noexcept {
   ensure_initialized();
   std::unique_ptr<GridCtx> c(new GridCtx);
-  c->grid.reset(new CommGrid(comm, nprow, npcol, order));
+  c->grid.reset(new CommGrid(world_of(comm), nprow, npcol, order));
   const int ctx = g_next_ctx--;
   g_grids[ctx] = std::move(c);
   return ctx;
@@ -535,7 +563,7 @@ void dlaf_free_all_grids(void) noexcept {
 char grid_ordering(DLAF_Comm comm, int nprow, int npcol, int myprow, int mypcol) noexcept {
   // src/c_api/grid.cpp:50-74: both predicates are AND-reduced over the communicator, column-major wins when both
   // hold, neither -> error exit.
-  const Comm* c = comm;
+  const Comm* c = world_of(comm);
   const int rank = c ? c->rank : 0;
   int flags[2] = {rank == myprow * npcol + mypcol ? 1 : 0, rank == mypcol * nprow + myprow ? 1 : 0};
   if (c != nullptr && c->nccl != nullptr && c->size > 1) {
@@ -607,6 +635,19 @@ long dlaf_b200_last_launch_count(int ctx) noexcept {
   if (c.last_type < 0 || !c.slot[c.last_type])
     return 0;
   return c.slot[c.last_type]->launches();
+}
+
+int dlaf_b200_rank_global_tile(long global_tile, int grid_size, int src_rank) noexcept {
+  return rank_global_tile(global_tile, grid_size, src_rank);
+}
+long dlaf_b200_local_tile_from_global_tile(long global_tile, int grid_size, int rank, int src_rank) noexcept {
+  return local_tile_from_global_tile(global_tile, grid_size, rank, src_rank);
+}
+long dlaf_b200_next_local_tile_from_global_tile(long global_tile, int grid_size, int rank, int src_rank) noexcept {
+  return next_local_tile_from_global_tile(global_tile, grid_size, rank, src_rank);
+}
+long dlaf_b200_global_tile_from_local_tile(long local_tile, int grid_size, int rank, int src_rank) noexcept {
+  return global_tile_from_local_tile(local_tile, grid_size, rank, src_rank);
 }
 
 int dlaf_b200_guard_fallback_steps(int ctx) noexcept {

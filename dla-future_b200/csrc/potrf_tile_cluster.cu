@@ -98,7 +98,7 @@ __device__ __forceinline__ double rsqrt_nr(double a) {
   return fma(y * 0.5, fma(-a * y, y, 1.0), y);
 }
 
-// Measurement aid: clock64 stamps of CTA 0 / thread 0 per panel step (tools/gpu_diag_tile_test): 4 per step
+// Measurement aid: clock64 stamps of CTA 0 / thread 0 per panel step (tools/gpu_diag_tile_test): 8 per step
 __device__ long long* g_tile_clock_trace = nullptr;
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
@@ -193,7 +193,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
     const int next_rank = (J + 1) % CL;
     const int jlJ = J / CL;
     if (trace)
-      trace[J * 4 + 0] = clock64();
+      trace[J * 8 + 0] = clock64();
     if (own) {
       double* pn = sm.P[J & 1];  // (holds panel J-2: dead)
       if (J > 0)
@@ -206,6 +206,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
         pn[(2 * tig) * PLD + 8 * I + g] = c.x;
         pn[(2 * tig + 1) * PLD + 8 * I + g] = c.y;
       }
+      if (trace)
+        trace[J * 8 + 1] = clock64();
       if (warp == (J & (NW - 1))) {
         // this warp holds the diagonal fragment: its lane 0 factorises the 8 x 8 pivot block right away (a chain of
         // rsqrt + dependent FMAs, everything in registers with static indices) while the other warps finish their rows
@@ -247,7 +249,11 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
           if (spin > (1u << 24))
             __trap();
       }
+      if (trace)
+        trace[J * 8 + 2] = clock64();
       __syncthreads();
+      if (trace)
+        trace[J * 8 + 3] = clock64();
       {
         // one panel row per thread: x <- x L_D^-T (forward substitution, columns left to right), in place; the finished
         // row goes to my own panel buffer, into the tile in global memory (result, and the medium the other CTAs read it
@@ -291,8 +297,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
       }
     }
     if (trace)
-      trace[J * 4 + 1] = clock64();
+      trace[J * 8 + 4] = clock64();
     cluster_arrive_release();  // (release at cluster scope: the global and DSMEM stores above are visible after the wait)
+    if (trace)
+      trace[J * 8 + 5] = clock64();
     if (J > 0) {
       update(sm.P[(J - 1) & 1], J - 1, own ? jlJ + 1 : 0, JL - 1);  // the rest (overlaps the owner's critical part)
       if (rank == (J + 2) % CL && J + 1 < nfc) {
@@ -303,7 +311,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
       }
     }
     if (trace)
-      trace[J * 4 + 2] = clock64();
+      trace[J * 8 + 6] = clock64();
     cluster_wait_acquire();  // panel J is published
     if (!own && rank != next_rank && has_next) {  // (the next owner got it by DSMEM)
       const int r = 8 * (J + 1) + tid;
@@ -316,7 +324,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
     }
     __syncthreads();
     if (trace)
-      trace[J * 4 + 3] = clock64();
+      trace[J * 8 + 7] = clock64();
   }
 
   // ================================ phase 2: inverses of the 128 x 128 diagonal blocks ================================

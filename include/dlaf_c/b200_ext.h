@@ -67,6 +67,14 @@ DLAF_EXTERN_C double dlaf_b200_check_cholesky_device_z(int ctx, char uplo, const
 /* Barrier over the ranks of the grid (the miniapp's MPI_Barrier / wait_all_communicators). */
 DLAF_EXTERN_C void dlaf_b200_grid_barrier(int ctx) DLAF_NOEXCEPT;
 
+/* 1-D block-cyclic index math the library uses (one tile per block), with the reference's signatures
+ * (include/dlaf/matrix/util_distribution.h:82-196): owner rank of a global tile, local index of a global tile on `rank`
+ * (-1 if not the owner), local index of the first tile of `rank` at or after a global tile, global index of a local tile. */
+DLAF_EXTERN_C int dlaf_b200_rank_global_tile(long global_tile, int grid_size, int src_rank) DLAF_NOEXCEPT;
+DLAF_EXTERN_C long dlaf_b200_local_tile_from_global_tile(long global_tile, int grid_size, int rank, int src_rank) DLAF_NOEXCEPT;
+DLAF_EXTERN_C long dlaf_b200_next_local_tile_from_global_tile(long global_tile, int grid_size, int rank, int src_rank) DLAF_NOEXCEPT;
+DLAF_EXTERN_C long dlaf_b200_global_tile_from_local_tile(long local_tile, int grid_size, int rank, int src_rank) DLAF_NOEXCEPT;
+
 /* Grid coordinates of this rank in ctx: out = {nprow, npcol, myprow, mypcol}. */
 DLAF_EXTERN_C void dlaf_b200_grid_info(int ctx, int out[4]) DLAF_NOEXCEPT;
 /* Rows / columns of the local part (reference: Distribution::local_size, src/matrix/distribution.cpp:117-150). */

@@ -47,6 +47,21 @@ def test_index_math_against_reference_table(oracle):
             assert oracle.global_tile_from_local_tile(c["local_tile"], c["grid_size"], c["rank"], c["src_rank"]) == c["global_tile"]
 
 
+def test_product_index_math_against_reference_table(pkg):
+    """The same golden table against the PRODUCT's index functions (csrc/distribution.h, exported through the C ABI and
+    used by the engine / C API for every owner / local-index computation)."""
+    L = pkg.lib()
+    with open(os.path.join(HERE, "golden", "util_distribution_cases.json")) as f:
+        g = json.load(f)
+    for row in g["cases"]:
+        c = dict(zip(g["keys"], row))
+        assert L.dlaf_b200_rank_global_tile(c["global_tile"], c["grid_size"], c["src_rank"]) == c["rank_tile"]
+        assert L.dlaf_b200_local_tile_from_global_tile(c["global_tile"], c["grid_size"], c["rank"], c["src_rank"]) == c["local_tile"]
+        assert L.dlaf_b200_next_local_tile_from_global_tile(c["global_tile"], c["grid_size"], c["rank"], c["src_rank"]) == c["local_tile_next"]
+        if c["local_tile"] >= 0:
+            assert L.dlaf_b200_global_tile_from_local_tile(c["local_tile"], c["grid_size"], c["rank"], c["src_rank"]) == c["global_tile"]
+
+
 def test_random_hpd_properties(oracle):
     """include/dlaf/util_matrix.h:410-453: Hermitian, real diagonal in [2N-1, 2N+1], |offdiag| <= 1,
     values independent of the tile size only through the per-tile seeds (same nb -> same matrix)."""

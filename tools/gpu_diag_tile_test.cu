@@ -90,24 +90,38 @@ int main() {
     std::printf("nbp %d: cluster tile kernel %.1f us avg, %.1f us best (round 1: 4 block kernels + 6 GEMM launches = 342 us at 512)\n", nbp,
                 total / (reps - 5) * 1000, best * 1000);
     if (nbp == 512) {
-      long long* dtr; cudaMalloc(&dtr, 64 * 4 * 8); cudaMemset(dtr, 0, 64 * 4 * 8);
+      long long* dtr; cudaMalloc(&dtr, 64 * 8 * 8); cudaMemset(dtr, 0, 64 * 8 * 8);
       potrf_tile_set_clock_trace(dtr);
       cudaMemcpy(dT, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
       launch_potrf_tile_cluster_f64(dT, ld, dW, nbp, dinfo, 0, 0);
       cudaDeviceSynchronize();
       potrf_tile_set_clock_trace(nullptr);
-      std::vector<long long> tr(64 * 4);
+      std::vector<long long> tr(64 * 8);
       cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost);
-      double own = 0, upd = 0, wait = 0; int nown = 0;
+      // stamps (CTA 0, thread 0): 0 step start | 1 own column updated + extracted | 2 factor done (thread 0 is the factor
+      // thread when J % 16 == 0) | 3 barrier after the factor | 4 row solve + stores issued | 5 arrived | 6 rest updated | 7 waited + read back
+      const char* nm[7] = {"upd+extract", "factor", "sync", "solve+stores", "arrive", "rest update", "wait+readback"};
+      double sum_own[7] = {0}, sum_oth[7] = {0}; int nown = 0, noth = 0;
       for (int J = 0; J < 64; ++J) {
-        if (J % 8 == 0) { own += double(tr[J * 4 + 1] - tr[J * 4]); ++nown; }
-        upd += double(tr[J * 4 + 2] - tr[J * 4 + 1]);
-        wait += double(tr[J * 4 + 3] - tr[J * 4 + 2]);
+        const bool own = (J % 8 == 0);
+        for (int q = 0; q < 7; ++q) {
+          long long a = tr[J * 8 + q], b = tr[J * 8 + q + 1];
+          if (!own && q < 4) continue;
+          if (!own && q == 4) a = tr[J * 8 + 0];
+          (own ? sum_own : sum_oth)[q] += double(b - a);
+        }
+        (own ? nown : noth)++;
       }
-      std::printf("phase clocks (CTA 0, thread 0): owner critical part %.0f clk avg over %d owned panels; update after arrive %.0f clk avg; "
-                  "barrier wait + panel read-back %.0f clk avg; whole phase 1 %.0f clk; per step", own / nown, nown, upd / 64, wait / 64,
-                  double(tr[63 * 4 + 3] - tr[0]));
-      for (int J = 0; J < 64; J += 9) std::printf(" [J=%d: %lld %lld %lld]", J, tr[J*4+1]-tr[J*4], tr[J*4+2]-tr[J*4+1], tr[J*4+3]-tr[J*4+2]);
+      std::printf("phase clocks, CTA 0 thread 0, whole phase 1 %.0f clk;  owned panels (avg of %d):", double(tr[63 * 8 + 7] - tr[0]), nown);
+      for (int q = 0; q < 7; ++q) std::printf(" %s %.0f", nm[q], sum_own[q] / nown);
+      std::printf(";  other panels (avg of %d):", noth);
+      for (int q = 4; q < 7; ++q) std::printf(" %s %.0f", nm[q], sum_oth[q] / noth);
+      std::printf("\n  owned panel J=0:");
+      for (int q = 0; q < 7; ++q) std::printf(" %lld", tr[q + 1] - tr[q]);
+      std::printf("   J=16:");
+      for (int q = 0; q < 7; ++q) std::printf(" %lld", tr[16 * 8 + q + 1] - tr[16 * 8 + q]);
+      std::printf("   J=8 (factor on another warp):");
+      for (int q = 0; q < 7; ++q) std::printf(" %lld", tr[8 * 8 + q + 1] - tr[8 * 8 + q]);
       std::printf("\n");
       cudaFree(dtr);
     }

@@ -33,7 +33,7 @@ void potrf_set_clock_trace(long long* dev_buffer);
 bool potrf_tile_cluster_supported(int nbp);
 void launch_potrf_tile_cluster_f64(double* T, long ldt, double* W, int nbp, int* info, int info_offset,
                                    cudaStream_t stream);
-// Measurement aid: device buffer of 64 * 8 clock64 stamps (CTA 0, thread 0, per panel step); nullptr = off.
+// Measurement aid: device buffer of 64 * 12 clock64 stamps (CTA 0, thread 0, per panel step); nullptr = off.
 void potrf_tile_set_clock_trace(long long* dev_buffer);
 
 // Per element type entry point: Cholesky + inverse of one Gran<T> x Gran<T> diagonal block.

@@ -45,23 +45,38 @@ constexpr int NW = 16;                 // warps per CTA
 constexpr int NTHR = NW * 32;          // 512
 constexpr int MAXNB = 512;             // largest tile
 constexpr int NFC = MAXNB / 8;         // block columns / fragment rows of the largest tile (64)
-constexpr int PLD = MAXNB + 8;         // panel copies are k-major: P[k * PLD + row]; PLD = 8 (mod 16) doubles
+// Panel copies are row-major, 64 bytes per row, entries permuted to [x0 x4 x1 x5 x2 x6 x3 x7] and the four 16-byte chunks of
+// a row XOR-swizzled with (row >> 1) & 3:
+//   * lane (g, tig) of a warp fetches BOTH DMMA operand halves of its row — (x_tig, x_{4+tig}) — with one LDS.128, and a
+//     quarter-warp (2 rows x 4 chunks) covers 128 contiguous bytes: conflict-free;
+//   * the thread that solves / reads back ONE row touches its 4 chunks at 64-byte stride; the swizzle spreads 8
+//     consecutive rows over all 8 16-byte bank groups (without it: 4-way conflicts, measured 4.5 clk per row);
+//   * rows 8 (J+1) .. of a panel are one contiguous byte range: ONE bulk DSMEM copy hands it to the next owner.
+__host__ __device__ constexpr int ppos(int k) { return (k & 3) * 2 + (k >> 2); }
+// index (in doubles) of chunk q (= entries x_q, x_{4+q}) of row `row`
+__host__ __device__ constexpr int pchunk(int row, int q) { return row * 8 + ((q ^ ((row >> 1) & 3)) << 1); }
+// index of entry k of row `row`
+__host__ __device__ constexpr int pidx(int row, int k) { return pchunk(row, ppos(k) >> 1) + (ppos(k) & 1); }
 constexpr int JL = NFC / CL;           // block columns per CTA (8)
 constexpr int GB = 128;                // diagonal blocks whose inverses the TRSM wants
 // fragments of CTA 0 (the most): block columns 0, 8, .., 56 with 64, 56, .., 8 fragment rows
 constexpr int MAXFRAGS = JL * (NFC + CL) / 2;  // 288
 
-// Shared memory of one CTA (214 KB): its part of the lower triangle as 8 x 8 DMMA accumulator fragments (64 doubles each,
-// lane-major: lane l owns doubles 2l, 2l+1 = row l/4, columns 2 (l%4), +1), two k-major panel buffers, the pivot factor.
+// Shared memory of one CTA (209 KB): its part of the lower triangle as 8 x 8 DMMA accumulator fragments (64 doubles each,
+// lane-major: lane l owns doubles 2l, 2l+1 = row l/4, columns 2 (l%4), +1), two panel buffers, the pivot factor.
 struct __align__(16) TileSmem {
   double frag[MAXFRAGS * 64];
-  double P[2][8 * PLD];   // finished panels J (parity J % 2); phase 2 reuses them (minv, scratch)
+  double P[2][8 * MAXNB];  // finished panels J (parity J % 2), layout above (pchunk / pidx); phase 2 reuses them
   double dfL[64];         // pivot block: strictly lower part of L_D (row-major a * 8 + b)
   double dfinv[8];        // 1 / diag(L_D)
   double dfpiv[8];        // the pivots themselves (their square roots are taken off the critical chain)
   // Written by the NEXT rank of the cluster (DSMEM): the highest panel index whose landing buffer over there is free,
   // i.e. this CTA may push panel J into P[J & 1] of rank (J + 1) % CL once free_for >= J.
   int free_for;
+  // mbarrier the PREVIOUS rank's bulk DSMEM copy of a panel into my panel buffer completes on (complete_tx): what the
+  // next owner waits for instead of the cluster barrier. (Per-thread st.shared::cluster pushes: 2016 16-byte remote
+  // stores cost 4.4-7k clk per panel; one cp.async.bulk moves the same 32 KB.)
+  unsigned long long mbar;
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -76,8 +91,31 @@ __device__ __forceinline__ unsigned map_to_rank(const void* local_smem, unsigned
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(rank));
   return ra;
 }
-__device__ __forceinline__ void st_cluster_f64(unsigned raddr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
+__device__ __forceinline__ unsigned smem_addr(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+// one bulk copy: my shared memory -> the same place in a peer CTA's shared memory, completion (bytes) on the peer's mbarrier
+__device__ __forceinline__ void bulk_copy_to_peer(unsigned dst_cluster, unsigned src_cta, unsigned bytes, unsigned mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_addr(bar);
+  for (unsigned spin = 0;; ++spin) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done)
+      return;
+    if (spin > (1u << 24))
+      __trap();
+  }
 }
 __device__ __forceinline__ void st_release_cluster_s32(unsigned raddr, int v) {
   asm volatile("st.release.cluster.shared::cluster.s32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory");
@@ -98,7 +136,7 @@ __device__ __forceinline__ double rsqrt_nr(double a) {
   return fma(y * 0.5, fma(-a * y, y, 1.0), y);
 }
 
-// Measurement aid: clock64 stamps of CTA 0 / thread 0 per panel step (tools/gpu_diag_tile_test): 8 per step
+// Measurement aid: clock64 stamps of CTA 0 / thread 0 per panel step (tools/gpu_diag_tile_test): 8 per step (+ 4 x 64 extra)
 __device__ long long* g_tile_clock_trace = nullptr;
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
@@ -142,24 +180,24 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
   __syncthreads();
 
   // applies panel `pb` (block column Jp) to my fragments of local block columns jl in [jl_lo, jl_hi] with Jc > Jp;
-  // rows are dealt to the warps round-robin (I % NW), so a warp loads the A operand of a fragment row once
+  // rows are dealt to the warps round-robin (I % NW), so a warp loads the A operands of a fragment row once
   auto update = [&](const double* __restrict__ pb, int Jp, int jl_lo, int jl_hi) {
     double b0[JL], b1[JL];
 #pragma unroll
     for (int jl = 0; jl < JL; ++jl) {
       const int Jc = rank + CL * jl;
       const bool on = (jl >= jl_lo && jl <= jl_hi && Jc > Jp && Jc < nfc);
-      b0[jl] = on ? pb[tig * PLD + 8 * Jc + g] : 0.0;
-      b1[jl] = on ? pb[(4 + tig) * PLD + 8 * Jc + g] : 0.0;
+      const double2 b = on ? *reinterpret_cast<const double2*>(&pb[pchunk(8 * Jc + g, tig)]) : make_double2(0.0, 0.0);
+      b0[jl] = b.x;
+      b1[jl] = b.y;
     }
     // two fragment rows per trip: two independent load -> DMMA -> DMMA -> store chains in flight per warp
+    // (measured and dropped: loading 8 fragments, then 16 DMMAs, then 8 stores per batch — slower, 3.3k vs 2.1k clk)
     for (int I = Jp + 1 + ((warp - (Jp + 1)) & (NW - 1)); I < nfc; I += 2 * NW) {  // I > Jp, I % NW == warp
       const int I2 = I + NW;
       const bool two = I2 < nfc;
-      const double a0 = -pb[tig * PLD + 8 * I + g];
-      const double a1 = -pb[(4 + tig) * PLD + 8 * I + g];
-      const double a2 = two ? -pb[tig * PLD + 8 * I2 + g] : 0.0;
-      const double a3 = two ? -pb[(4 + tig) * PLD + 8 * I2 + g] : 0.0;
+      const double2 a = *reinterpret_cast<const double2*>(&pb[pchunk(8 * I + g, tig)]);
+      const double2 a2 = two ? *reinterpret_cast<const double2*>(&pb[pchunk(8 * I2 + g, tig)]) : make_double2(0.0, 0.0);
 #pragma unroll
       for (int jl = 0; jl < JL; ++jl) {
         const int Jc = rank + CL * jl;
@@ -169,10 +207,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
           double2* f2 = reinterpret_cast<double2*>(&sm.frag[(fo[jl] + I2 - Jc) * 64 + 2 * lane]);
           double2 c = first ? *f : make_double2(0.0, 0.0);
           double2 d = second ? *f2 : make_double2(0.0, 0.0);
-          dmma884(c.x, c.y, a0, b0[jl]);
-          dmma884(d.x, d.y, a2, b0[jl]);
-          dmma884(c.x, c.y, a1, b1[jl]);
-          dmma884(d.x, d.y, a3, b1[jl]);
+          dmma884(c.x, c.y, -a.x, b0[jl]);
+          dmma884(d.x, d.y, -a2.x, b0[jl]);
+          dmma884(c.x, c.y, -a.y, b1[jl]);
+          dmma884(d.x, d.y, -a2.y, b1[jl]);
           if (first)
             *f = c;
           if (second)
@@ -183,28 +221,45 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
   };
 
   // ================================ phase 1: the factor, panel by panel ================================
-  if (tid == 0)
+  // Hand-over of panel J:  owner J --(one bulk DSMEM copy completing on the receiver's mbarrier)--> next owner (critical path);
+  //                        owner J --(global memory + cluster barrier J)--> everybody else (reads it back from L2).
+  // Barrier phases: every CTA arrives at barrier J in iteration J; the next owner postpones its WAIT on barrier J until
+  // just before it arrives at barrier J+1 (it does not need barrier J: its copy of panel J came by DSMEM).
+  if (tid == 0) {
     sm.free_for = 1;  // the landing buffers of panels 0 and 1 have never been used
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sm.mbar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   cluster_arrive_release();
-  cluster_wait_acquire();  // every CTA's flag is initialised before a peer may write it
+  cluster_wait_acquire();  // every CTA's flag / mbarrier is initialised before a peer may touch it
   for (int J = 0; J < nfc; ++J) {
     const bool own = (rank == J % CL);
     const bool has_next = (J + 1 < nfc);
     const int next_rank = (J + 1) % CL;
+    const bool is_next = has_next && rank == next_rank;
     const int jlJ = J / CL;
     if (trace)
       trace[J * 8 + 0] = clock64();
     if (own) {
       double* pn = sm.P[J & 1];  // (holds panel J-2: dead)
-      if (J > 0)
-        update(sm.P[(J - 1) & 1], J - 1, jlJ, jlJ);  // my block column J first: it is the critical path
-      // fragments of block column J -> raw panel, k-major, straight into the buffer the finished panel will occupy; same
-      // row -> warp mapping as the update, so no barrier in between
-      const int foJ = foff(jlJ);  // (fo[] stays statically indexed: registers, not local memory)
-      for (int I = J + ((warp - J) & (NW - 1)); I < nfc; I += NW) {
-        const double2 c = *reinterpret_cast<const double2*>(&sm.frag[(foJ + I - J) * 64 + 2 * lane]);
-        pn[(2 * tig) * PLD + 8 * I + g] = c.x;
-        pn[(2 * tig + 1) * PLD + 8 * I + g] = c.y;
+      const double* pp = sm.P[(J - 1) & 1];
+      // My block column J: apply panel J-1 (it is the critical path) and write the raw column straight into the buffer the
+      // finished panel will occupy — the fragments of a factorised column are never needed again.
+      {
+        const int foJ = foff(jlJ);  // (fo[] stays statically indexed: registers, not local memory)
+        double2 bJ = make_double2(0.0, 0.0);
+        if (J > 0)
+          bJ = *reinterpret_cast<const double2*>(&pp[pchunk(8 * J + g, tig)]);
+        for (int I = J + ((warp - J) & (NW - 1)); I < nfc; I += NW) {
+          double2 c = *reinterpret_cast<const double2*>(&sm.frag[(foJ + I - J) * 64 + 2 * lane]);
+          if (J > 0) {
+            const double2 a = *reinterpret_cast<const double2*>(&pp[pchunk(8 * I + g, tig)]);
+            dmma884(c.x, c.y, -a.x, bJ.x);
+            dmma884(c.x, c.y, -a.y, bJ.y);
+          }
+          pn[pidx(8 * I + g, 2 * tig)] = c.x;
+          pn[pidx(8 * I + g, 2 * tig + 1)] = c.y;
+        }
       }
       if (trace)
         trace[J * 8 + 1] = clock64();
@@ -218,7 +273,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
           for (int b = 0; b < 8; ++b)
 #pragma unroll
             for (int a = 0; a < 8; ++a)
-              D[a][b] = (a >= b) ? pn[b * PLD + 8 * J + a] : 0.0;
+              D[a][b] = (a >= b) ? pn[pidx(8 * J + a, b)] : 0.0;
           int fail = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -254,51 +309,71 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
       __syncthreads();
       if (trace)
         trace[J * 8 + 3] = clock64();
-      {
-        // one panel row per thread: x <- x L_D^-T (forward substitution, columns left to right), in place; the finished
-        // row goes to my own panel buffer, into the tile in global memory (result, and the medium the other CTAs read it
-        // back from) and straight into the panel buffer of the NEXT owner (DSMEM), who therefore never waits for L2
-        const int r = 8 * (J + 1) + tid;
-        if (r < nbp) {
-          double x[8], Lm[8][8], invd[8];
+      // one panel row per thread: x <- x L_D^-T (forward substitution, columns left to right), in place in my own panel
+      // buffer; the whole panel then goes to the NEXT owner's buffer with one bulk DSMEM copy
+      const int r = 8 * (J + 1) + tid;
+      double x[8];
+      if (r < nbp) {
+        double Lm[8][8], invd[8];
 #pragma unroll
-          for (int a = 0; a < 8; ++a) {
-            invd[a] = sm.dfinv[a];
+        for (int a = 0; a < 8; ++a) {
+          invd[a] = sm.dfinv[a];
 #pragma unroll
-            for (int b = 0; b < 8; ++b)
-              Lm[a][b] = (a > b) ? sm.dfL[a * 8 + b] : 0.0;
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            x[k] = pn[k * PLD + r];
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            x[s] *= invd[s];
-#pragma unroll
-            for (int t = s + 1; t < 8; ++t)
-              x[t] = fma(-x[s], Lm[t][s], x[t]);
-          }
-          const unsigned remote = has_next ? map_to_rank(&pn[r], static_cast<unsigned>(next_rank)) : 0u;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            pn[k * PLD + r] = x[k];
-            if (has_next)
-              st_cluster_f64(remote + static_cast<unsigned>(k * PLD * sizeof(double)), x[k]);
-            T[r + static_cast<long>(8 * J + k) * ldt] = x[k];  // coalesced along r
-          }
+          for (int b = 0; b < 8; ++b)
+            Lm[a][b] = (a > b) ? sm.dfL[a * 8 + b] : 0.0;
         }
-        if (tid < 64) {  // the pivot block itself: strictly lower part from the factor, diagonal = correctly rounded sqrt
-          const int a = tid >> 3, b = tid & 7;
-          if (a > b)
-            T[(8 * J + a) + static_cast<long>(8 * J + b) * ldt] = sm.dfL[a * 8 + b];
-          else if (a == b)
-            T[static_cast<long>(8 * J + a) * (1 + ldt)] = sqrt(sm.dfpiv[a]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double2 v = *reinterpret_cast<const double2*>(&pn[pchunk(r, q)]);
+          x[q] = v.x;
+          x[4 + q] = v.y;
         }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          x[s] *= invd[s];
+#pragma unroll
+          for (int t = s + 1; t < 8; ++t)
+            x[t] = fma(-x[s], Lm[t][s], x[t]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<double2*>(&pn[pchunk(r, q)]) = make_double2(x[q], x[4 + q]);
       }
+      if (trace)
+        trace[512 + J * 4 + 0] = clock64();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my rows are visible to the bulk-copy engine
+      if (trace)
+        trace[512 + J * 4 + 1] = clock64();
+      __syncthreads();
+      if (trace)
+        trace[512 + J * 4 + 2] = clock64();
+      if (tid == 0 && has_next) {
+        // rows 8 (J+1) .. nbp-1 of the panel are contiguous: ONE bulk copy into the same place of the next owner's buffer
+        double* first = &pn[8 * (J + 1) * 8];
+        bulk_copy_to_peer(map_to_rank(first, static_cast<unsigned>(next_rank)), smem_addr(first),
+                          static_cast<unsigned>((nbp - 8 * (J + 1)) * 8 * sizeof(double)),
+                          map_to_rank(&sm.mbar, static_cast<unsigned>(next_rank)));
+      }
+      if (trace)
+        trace[J * 8 + 4] = clock64();
+      // ... and only now, off the critical path, into the tile in global memory: the result, and the medium the other
+      // CTAs read the panel back from after the cluster barrier
+      if (r < nbp) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          T[r + static_cast<long>(8 * J + k) * ldt] = x[k];  // coalesced along r
+      }
+      if (tid < 64) {  // the pivot block itself: strictly lower part from the factor, diagonal = correctly rounded sqrt
+        const int a = tid >> 3, b = tid & 7;
+        if (a > b)
+          T[(8 * J + a) + static_cast<long>(8 * J + b) * ldt] = sm.dfL[a * 8 + b];
+        else if (a == b)
+          T[static_cast<long>(8 * J + a) * (1 + ldt)] = sqrt(sm.dfpiv[a]);
+      }
+      if (J > 0)
+        cluster_wait_acquire();  // my postponed wait on barrier J-1 (I was the "next owner" of iteration J-1)
     }
-    if (trace)
-      trace[J * 8 + 4] = clock64();
-    cluster_arrive_release();  // (release at cluster scope: the global and DSMEM stores above are visible after the wait)
+    cluster_arrive_release();  // barrier J (release at cluster scope: the global stores above are visible after the wait)
     if (trace)
       trace[J * 8 + 5] = clock64();
     if (J > 0) {
@@ -312,14 +387,28 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
     }
     if (trace)
       trace[J * 8 + 6] = clock64();
-    cluster_wait_acquire();  // panel J is published
-    if (!own && rank != next_rank && has_next) {  // (the next owner got it by DSMEM)
-      const int r = 8 * (J + 1) + tid;
-      if (r < nbp) {
-        double* pn = sm.P[J & 1];
+    if (is_next) {
+      // next owner: panel J arrives by bulk DSMEM copy; barrier J is waited for later (see above)
+      if (tid == 0) {
+        const unsigned bytes = static_cast<unsigned>((nbp - 8 * (J + 1)) * 8 * sizeof(double));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&sm.mbar)), "r"(bytes) : "memory");
+      }
+      mbar_wait_parity(&sm.mbar, static_cast<unsigned>((J / CL) & 1));  // every thread observes the completion itself
+    }
+    else {
+      cluster_wait_acquire();  // panel J is published in global memory
+      if (!own && has_next) {
+        const int r = 8 * (J + 1) + tid;
+        if (r < nbp) {
+          double* pn = sm.P[J & 1];
+          double x[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          pn[k * PLD + r] = __ldcg(T + r + static_cast<long>(8 * J + k) * ldt);
+          for (int k = 0; k < 8; ++k)
+            x[k] = __ldcg(T + r + static_cast<long>(8 * J + k) * ldt);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<double2*>(&pn[pchunk(r, q)]) = make_double2(x[q], x[4 + q]);
+        }
       }
     }
     __syncthreads();

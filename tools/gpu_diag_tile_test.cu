@@ -90,13 +90,13 @@ int main() {
     std::printf("nbp %d: cluster tile kernel %.1f us avg, %.1f us best (round 1: 4 block kernels + 6 GEMM launches = 342 us at 512)\n", nbp,
                 total / (reps - 5) * 1000, best * 1000);
     if (nbp == 512) {
-      long long* dtr; cudaMalloc(&dtr, 64 * 8 * 8); cudaMemset(dtr, 0, 64 * 8 * 8);
+      long long* dtr; cudaMalloc(&dtr, 64 * 12 * 8); cudaMemset(dtr, 0, 64 * 12 * 8);
       potrf_tile_set_clock_trace(dtr);
       cudaMemcpy(dT, A.data(), A.size() * 8, cudaMemcpyHostToDevice);
       launch_potrf_tile_cluster_f64(dT, ld, dW, nbp, dinfo, 0, 0);
       cudaDeviceSynchronize();
       potrf_tile_set_clock_trace(nullptr);
-      std::vector<long long> tr(64 * 8);
+      std::vector<long long> tr(64 * 12);
       cudaMemcpy(tr.data(), dtr, tr.size() * 8, cudaMemcpyDeviceToHost);
       // stamps (CTA 0, thread 0): 0 step start | 1 own column updated + extracted | 2 factor done (thread 0 is the factor
       // thread when J % 16 == 0) | 3 barrier after the factor | 4 row solve + stores issued | 5 arrived | 6 rest updated | 7 waited + read back
@@ -122,6 +122,9 @@ int main() {
       for (int q = 0; q < 7; ++q) std::printf(" %lld", tr[16 * 8 + q + 1] - tr[16 * 8 + q]);
       std::printf("   J=8 (factor on another warp):");
       for (int q = 0; q < 7; ++q) std::printf(" %lld", tr[8 * 8 + q + 1] - tr[8 * 8 + q]);
+      std::printf("\n  inside solve+stores (owned panels J=0,16,32,48: my solve | proxy fence | barrier): ");
+      for (int J = 0; J < 64; J += 16)
+        std::printf("[%lld | %lld | %lld] ", tr[512 + J * 4 + 0] - tr[J * 8 + 3], tr[512 + J * 4 + 1] - tr[512 + J * 4 + 0], tr[512 + J * 4 + 2] - tr[512 + J * 4 + 1]);
       std::printf("\n");
       cudaFree(dtr);
     }

@@ -128,6 +128,9 @@ __device__ __forceinline__ int ld_acquire_cluster_s32(const int* p) {
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() {  // nothing to publish: no MEMBAR.ALL.GPU (~1k clk) in front
+  asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_wait_acquire() {
   asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
@@ -198,24 +201,36 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
       const bool two = I2 < nfc;
       const double2 a = *reinterpret_cast<const double2*>(&pb[pchunk(8 * I + g, tig)]);
       const double2 a2 = two ? *reinterpret_cast<const double2*>(&pb[pchunk(8 * I2 + g, tig)]) : make_double2(0.0, 0.0);
+      // software-pipelined over the local columns: the fragments of column jl+1 are loaded BEFORE those of column jl are
+      // stored (the compiler keeps shared-memory loads behind earlier stores to the fragment array), so the LDS latency
+      // overlaps the two dependent DMMAs of the current column
+      auto act = [&](int jl) { const int Jc = rank + CL * jl; return jl < JL && jl >= jl_lo && jl <= jl_hi && Jc > Jp && Jc <= I2 && Jc < nfc; };
+      auto ldf = [&](int jl, double2& c, double2& d) {
+        const int Jc = rank + CL * jl;
+        c = (Jc <= I) ? *reinterpret_cast<const double2*>(&sm.frag[(fo[jl] + I - Jc) * 64 + 2 * lane]) : make_double2(0.0, 0.0);
+        d = two ? *reinterpret_cast<const double2*>(&sm.frag[(fo[jl] + I2 - Jc) * 64 + 2 * lane]) : make_double2(0.0, 0.0);
+      };
+      double2 c = make_double2(0.0, 0.0), d = c, cn = c, dn = c;
+      if (act(0))
+        ldf(0, c, d);
 #pragma unroll
       for (int jl = 0; jl < JL; ++jl) {
-        const int Jc = rank + CL * jl;
-        if (jl >= jl_lo && jl <= jl_hi && Jc > Jp && Jc <= I2 && Jc < nfc) {  // warp-uniform
-          const bool first = (Jc <= I), second = two;
-          double2* f = reinterpret_cast<double2*>(&sm.frag[(fo[jl] + I - Jc) * 64 + 2 * lane]);
-          double2* f2 = reinterpret_cast<double2*>(&sm.frag[(fo[jl] + I2 - Jc) * 64 + 2 * lane]);
-          double2 c = first ? *f : make_double2(0.0, 0.0);
-          double2 d = second ? *f2 : make_double2(0.0, 0.0);
+        const bool cur = act(jl);         // warp-uniform
+        if (jl + 1 < JL && act(jl + 1))
+          ldf(jl + 1, cn, dn);
+        if (cur) {
+          const int Jc = rank + CL * jl;
           dmma884(c.x, c.y, -a.x, b0[jl]);
           dmma884(d.x, d.y, -a2.x, b0[jl]);
           dmma884(c.x, c.y, -a.y, b1[jl]);
           dmma884(d.x, d.y, -a2.y, b1[jl]);
-          if (first)
-            *f = c;
-          if (second)
-            *f2 = d;
+          if (Jc <= I)
+            *reinterpret_cast<double2*>(&sm.frag[(fo[jl] + I - Jc) * 64 + 2 * lane]) = c;
+          if (two)
+            *reinterpret_cast<double2*>(&sm.frag[(fo[jl] + I2 - Jc) * 64 + 2 * lane]) = d;
         }
+        c = cn;
+        d = dn;
       }
     }
   };
@@ -373,7 +388,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NTHR, 1)
       if (J > 0)
         cluster_wait_acquire();  // my postponed wait on barrier J-1 (I was the "next owner" of iteration J-1)
     }
-    cluster_arrive_release();  // barrier J (release at cluster scope: the global stores above are visible after the wait)
+    if (own)
+      cluster_arrive_release();  // barrier J (release at cluster scope: my global stores are visible after the wait)
+    else
+      cluster_arrive_relaxed();
     if (trace)
       trace[J * 8 + 5] = clock64();
     if (J > 0) {

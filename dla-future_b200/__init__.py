@@ -38,6 +38,7 @@ C_API_SYMBOLS = [
     "dlaf_b200_ozaki_pairs",
     "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops", "dlaf_b200_measure_int8_tensor_peak_tops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
+    *[f"dlaf_b200_triangular_solver_{t}" for t in "sdcz"], "dlaf_b200_last_solver_launch_count",
     "dlaf_b200_rank_global_tile", "dlaf_b200_local_tile_from_global_tile", "dlaf_b200_next_local_tile_from_global_tile",
     "dlaf_b200_global_tile_from_local_tile",
 ]
@@ -135,6 +136,9 @@ def lib() -> ctypes.CDLL:
         f = getattr(L, f"dlaf_b200_check_cholesky_{t}")
         f.argtypes = [ci, cc, vp, vp, DLAF_descriptor]
         f.restype = ctypes.c_double
+        f = getattr(L, f"dlaf_b200_triangular_solver_{t}")
+        f.argtypes = [ci, cc, cc, cc, cc, vp, vp, DLAF_descriptor, vp, DLAF_descriptor]
+        f.restype = ci
         f = getattr(L, f"dlaf_b200_check_cholesky_device_{t}")
         f.argtypes = [ci, cc, vp, vp, DLAF_descriptor, vp]
         f.restype = ctypes.c_double
@@ -142,6 +146,8 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_grid_barrier.restype = None
     L.dlaf_b200_wait.argtypes = [ci, vp]
     L.dlaf_b200_wait.restype = ci
+    L.dlaf_b200_last_solver_launch_count.argtypes = [ci]
+    L.dlaf_b200_last_solver_launch_count.restype = ctypes.c_long
     L.dlaf_b200_guard_fallback_steps.argtypes = [ci]
     L.dlaf_b200_guard_fallback_steps.restype = ci
     L.dlaf_b200_ozaki_pairs.restype = ci
@@ -281,6 +287,26 @@ def wait(ctx: int, stream: int = 0) -> int:
 
 def last_launch_count(ctx: int) -> int:
     return lib().dlaf_b200_last_launch_count(ctx)
+
+
+def triangular_solver(ctx: int, side: str, uplo: str, op: str, diag: str, alpha, a: np.ndarray, b: np.ndarray, mb: int, nb: int,
+                      m: int | None = None, n: int | None = None, isrc: int = 0, jsrc: int = 0) -> None:
+    """dlaf::triangular_solver through the C ABI: op(A) X = alpha B (side 'L') or X op(A) = alpha B (side 'R'); `a`, `b` are
+    this rank's HOST local parts (column-major numpy arrays), `b` is overwritten with X. B is m x n with blocks mb x nb, A is
+    square of order m (Left, blocks mb) or n (Right, blocks nb)."""
+    m = b.shape[0] if m is None else m
+    n = b.shape[1] if n is None else n
+    left = side.upper() == "L"
+    na, ba = (m, mb) if left else (n, nb)
+    da = DLAF_descriptor(na, na, ba, ba, isrc, jsrc, 0, 0, max(1, _ld_of(a)))
+    db = DLAF_descriptor(m, n, mb, nb, isrc, jsrc, 0, 0, max(1, _ld_of(b)))
+    al = np.array([alpha], dtype=b.dtype)
+    f = getattr(lib(), f"dlaf_b200_triangular_solver_{type_char(b.dtype)}")
+    f(ctx, side.encode(), uplo.encode(), op.encode(), diag.encode(), al.ctypes.data, a.ctypes.data, da, b.ctypes.data, db)
+
+
+def last_solver_launch_count(ctx: int) -> int:
+    return lib().dlaf_b200_last_solver_launch_count(ctx)
 
 
 def guard_fallback_steps(ctx: int) -> int:

@@ -21,6 +21,7 @@
 #include "common.h"
 #include "distribution.h"
 #include "engine.h"
+#include "trsm_engine.h"
 #include "util_matrix.h"
 
 using namespace dlaf_b200;
@@ -87,6 +88,7 @@ struct GridCtx {
   bool profiling = false;
   cudaStream_t stream = nullptr;  // stream of the synchronous host API
   int* d_red = nullptr;           // info reduction buffer
+  long last_solver_launches = 0;  // kernels launched by the last triangular solve
   ~GridCtx() {
     for (auto& s : slot)
       s.reset();
@@ -451,6 +453,68 @@ double check_cholesky(int ctx, char uplo, const T* a, const T* f, const DLAF_des
   return r;
 }
 
+// dlaf::triangular_solver on HOST local parts (the reference's MatrixMirror bracket around the GPU algorithm): a = local
+// part of the triangular matrix (read only), b = local part of the right-hand sides, overwritten with the solution.
+template <class T>
+int triangular_solver_host(int ctx, char side, char uplo, char op, char diag, const T* alpha, const T* a,
+                           const DLAF_descriptor& da, T* b, const DLAF_descriptor& db) {
+  using D = devtype_t<T>;
+  ensure_device();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return 0;
+  const CommGrid& g = *c.grid;
+  const bool left = (side == 'L' || side == 'l');
+  DLAF_B200_ASSERT(left || side == 'R' || side == 'r', "side must be L or R");
+  DLAF_B200_ASSERT(uplo == 'L' || uplo == 'l' || uplo == 'U' || uplo == 'u', "uplo must be L or U");
+  DLAF_B200_ASSERT(diag == 'N' || diag == 'n' || diag == 'U' || diag == 'u', "diag must be N or U");
+  // preconditions of the reference (solver/triangular.h:36-45, :89-97): square A with square blocks, conformable B,
+  // both on this grid with the same source rank
+  DLAF_B200_ASSERT(da.m == da.n && da.mb == da.nb, "the triangular matrix must be square with square blocks");
+  DLAF_B200_ASSERT(left ? (da.m == db.m && da.mb == db.mb) : (da.m == db.n && da.mb == db.nb), "A and B are not conformable");
+  DLAF_B200_ASSERT(da.i == 0 && da.j == 0 && db.i == 0 && db.j == 0, "sub-matrix offsets must be 0");
+  DLAF_B200_ASSERT(da.isrc == db.isrc && da.jsrc == db.jsrc && da.isrc >= 0 && da.isrc < g.P && da.jsrc >= 0 && da.jsrc < g.Q,
+                   "source rank");
+  TrsmProblem p;
+  p.side = side;
+  p.uplo = uplo;
+  p.op = op;
+  p.diag = diag;
+  p.m = db.m;
+  p.n = db.n;
+  p.mb = db.mb;
+  p.nb = db.nb;
+  p.P = g.P;
+  p.Q = g.Q;
+  p.prow = (g.row - da.isrc + g.P) % g.P;
+  p.pcol = (g.col - da.jsrc + g.Q) % g.Q;
+  p.src_row = da.isrc;
+  p.src_col = da.jsrc;
+  const long na = da.n;
+  const long lra = local_size_1d(na, da.nb, g.P, p.prow), lca = local_size_1d(na, da.nb, g.Q, p.pcol);
+  const long lrb = local_size_1d(db.m, db.mb, g.P, p.prow), lcb = local_size_1d(db.n, db.nb, g.Q, p.pcol);
+  DLAF_B200_ASSERT(da.ld >= std::max<long>(1, lra) && db.ld >= std::max<long>(1, lrb), "leading dimension smaller than local rows");
+  cudaStream_t s = ctx_stream(c);
+  D *dA = nullptr, *dB = nullptr;
+  const long ldA = std::max<long>(lra, 1), ldB = std::max<long>(lrb, 1);
+  if (lra > 0 && lca > 0) {
+    DLAF_CUDA_CHECK(cudaMalloc(&dA, sizeof(D) * ldA * lca));
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dA, sizeof(D) * ldA, a, sizeof(D) * da.ld, sizeof(D) * lra, lca, cudaMemcpyHostToDevice, s));
+  }
+  if (lrb > 0 && lcb > 0) {
+    DLAF_CUDA_CHECK(cudaMalloc(&dB, sizeof(D) * ldB * lcb));
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dB, sizeof(D) * ldB, b, sizeof(D) * db.ld, sizeof(D) * lrb, lcb, cudaMemcpyHostToDevice, s));
+  }
+  const std::complex<double> al(*alpha);
+  c.last_solver_launches = triangular_solve_device<D>(p, al.real(), al.imag(), dA, ldA, dB, ldB, g.row_comm, g.col_comm, s);
+  if (lrb > 0 && lcb > 0)
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(b, sizeof(D) * db.ld, dB, sizeof(D) * ldB, sizeof(D) * lrb, lcb, cudaMemcpyDeviceToHost, s));
+  DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(dA);
+  cudaFree(dB);
+  return 0;
+}
+
 template <class T>
 void random_hpd(int ctx, T* a, const DLAF_descriptor& desc) {
   ensure_initialized();
@@ -611,6 +675,11 @@ struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int 
                                         struct DLAF_descriptor d) noexcept {                                  \
     return check_cholesky<T>(ctx, uplo, a, f, d);                                                             \
   }                                                                                                           \
+  int dlaf_b200_triangular_solver_##sfx(int ctx, char side, char uplo, char op, char diag, const T* alpha,    \
+                                        const T* a, struct DLAF_descriptor da, T* b,                          \
+                                        struct DLAF_descriptor db) noexcept {                                 \
+    return triangular_solver_host<T>(ctx, side, uplo, op, diag, alpha, a, da, b, db);                         \
+  }                                                                                                           \
   double dlaf_b200_check_cholesky_device_##sfx(int ctx, char uplo, const T* a_dev, const T* f_dev,            \
                                                struct DLAF_descriptor d, void* stream) noexcept {             \
     return check_cholesky_device<T>(ctx, uplo, a_dev, f_dev, d, static_cast<cudaStream_t>(stream));           \
@@ -648,6 +717,10 @@ long dlaf_b200_next_local_tile_from_global_tile(long global_tile, int grid_size,
 }
 long dlaf_b200_global_tile_from_local_tile(long local_tile, int grid_size, int rank, int src_rank) noexcept {
   return global_tile_from_local_tile(local_tile, grid_size, rank, src_rank);
+}
+
+long dlaf_b200_last_solver_launch_count(int ctx) noexcept {
+  return grid_from_context(ctx).last_solver_launches;
 }
 
 int dlaf_b200_guard_fallback_steps(int ctx) noexcept {

@@ -28,4 +28,16 @@ inline long global_tile_from_local_tile(long local_tile, int grid_size, int rank
   return local_tile * grid_size + v;
 }
 
+// Number of elements of one dimension (global size n, block nb) held by virtual rank v of `grid_size`
+// (src/matrix/distribution.cpp:117-150: local tiles x block minus the shortfall of the ragged last tile if it is mine).
+inline long local_size_1d(long n, int nb, int grid_size, int v) {
+  if (n <= 0)
+    return 0;
+  const long nt = (n + nb - 1) / nb;
+  long s = next_local_tile_from_global_tile(nt, grid_size, v, 0) * nb;
+  if ((nt - 1) % grid_size == v)
+    s -= nt * nb - n;
+  return s;
+}
+
 }  // namespace dlaf_b200

@@ -90,14 +90,9 @@ void launch_gemm_nt_f64_if(const GemmArgs& a, const int* flag, cudaStream_t stre
   DLAF_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_trsm_fused_f64(const TrsmFusedArgs& a, int m, cudaStream_t stream) {
-  using Cfg = GemmCfg32x128w4;
-  if (m <= 0 || a.ns <= 0)
-    return;
-  DLAF_B200_ASSERT(m % Cfg::BM == 0, "fused TRSM: rows must be a multiple of the CTA row block");
-  DLAF_B200_ASSERT(a.ldb % 2 == 0 && a.ldt % 2 == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0 &&
-                       (reinterpret_cast<uintptr_t>(a.T) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
-                   "fused TRSM: 16-byte aligned operands");
+namespace {
+template <class Cfg>
+void launch_trsm_cfg(const TrsmFusedArgs& a, int m, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     DLAF_CUDA_CHECK(cudaFuncSetAttribute(trsm_fused_f64_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -106,6 +101,27 @@ void launch_trsm_fused_f64(const TrsmFusedArgs& a, int m, cudaStream_t stream) {
   }
   trsm_fused_f64_kernel<Cfg><<<m / Cfg::BM, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
   DLAF_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+void launch_trsm_fused_f64(const TrsmFusedArgs& a, int m, cudaStream_t stream) {
+  if (m <= 0 || a.ns <= 0)
+    return;
+  DLAF_B200_ASSERT(m % 32 == 0, "fused TRSM: rows must be a multiple of 32");
+  DLAF_B200_ASSERT(a.ldb % 2 == 0 && a.ldt % 2 == 0 && (reinterpret_cast<uintptr_t>(a.B) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(a.T) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+                   "fused TRSM: 16-byte aligned operands");
+  // Short panels (the single critical tile of the two-chain schedule: 512 rows) are bound by the DMMA rate of the few SMs
+  // they occupy (16 CTAs x 4 sequential substitution phases = 75 us): 16-row CTAs put them on twice as many SMs.
+  // DLAF_B200_TRSM_BM=32 keeps the 32-row CTAs everywhere.
+  static const bool small_ok = [] {
+    const char* e = std::getenv("DLAF_B200_TRSM_BM");
+    return e == nullptr || std::atoi(e) != 32;
+  }();
+  if (small_ok && m <= 2048)
+    launch_trsm_cfg<GemmCfg16x128w4>(a, m, stream);
+  else
+    launch_trsm_cfg<GemmCfg32x128w4>(a, m, stream);
 }
 
 template <>

@@ -346,6 +346,7 @@ using GemmCfg128x64 = GemmCfg<128, 64, 16, 4, 2>;
 using GemmCfg64w4s3 = GemmCfg<64, 64, 16, 3, 4, 2, 2>;
 using GemmCfg64w4s4 = GemmCfg<64, 64, 16, 4, 3, 2, 2>;
 using GemmCfg32x128w4 = GemmCfg<32, 128, 16, 3, 4, 1, 4>;  // in-place products (one CTA owns all 128 columns)
+using GemmCfg16x128w4 = GemmCfg<16, 128, 16, 3, 4, 1, 4>;  // same, half the rows per CTA: twice the CTAs for short panels
 
 // Host launcher (defined in gemm_dmma.cu): picks the tile configuration.
 void launch_gemm_nt_f64(const GemmArgs& args, cudaStream_t stream);

@@ -20,6 +20,19 @@ DLAF_EXTERN_C int dlaf_b200_cholesky_factorization_device_z(int ctx, char uplo, 
 /* Synchronise the stream and return the LAPACK-style info of the last factorization issued on ctx
  * (max over the ranks of the grid). */
 DLAF_EXTERN_C int dlaf_b200_wait(int ctx, void* cuda_stream) DLAF_NOEXCEPT;
+/* dlaf::triangular_solver (include/dlaf/solver/triangular.h:31-134; the reference has no C entry for it): solves
+ *   op(A) X = alpha B  (side 'L')   or   X op(A) = alpha B  (side 'R')
+ * for a triangular A (uplo 'L' / 'U', diag 'N' / 'U', op 'N' / 'T' / 'C') distributed like B on the grid of ctx; a and b are
+ * this rank's HOST local parts (column-major, leading dimensions in the descriptors), b is overwritten with X. A is m x m
+ * (Left) or n x n (Right) with square blocks equal to B's row (Left) / column (Right) block; same source rank. Collective
+ * over the grid, synchronous. alpha is passed by address. Returns 0. */
+DLAF_EXTERN_C int dlaf_b200_triangular_solver_s(int ctx, char side, char uplo, char op, char diag, const float* alpha, const float* a, struct DLAF_descriptor desca, float* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_triangular_solver_d(int ctx, char side, char uplo, char op, char diag, const double* alpha, const double* a, struct DLAF_descriptor desca, double* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_triangular_solver_c(int ctx, char side, char uplo, char op, char diag, const dlaf_complex_c* alpha, const dlaf_complex_c* a, struct DLAF_descriptor desca, dlaf_complex_c* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_triangular_solver_z(int ctx, char side, char uplo, char op, char diag, const dlaf_complex_z* alpha, const dlaf_complex_z* a, struct DLAF_descriptor desca, dlaf_complex_z* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+/* Number of this library's kernel launches issued by the last triangular solve on ctx. */
+DLAF_EXTERN_C long dlaf_b200_last_solver_launch_count(int ctx) DLAF_NOEXCEPT;
+
 /* fp64 only. The trailing update runs as exact int8 digit products on tcgen05 (DLAF_B200_D_BULK=ozaki, default) with a
  * data-dependent guard: a step whose panel has a row spanning more than ~40 binades (an entry would keep fewer than
  * DLAF_B200_OZAKI_MIN_BITS = 16 significant bits) is updated by the native fp64 (DMMA) kernel instead. Returns the

@@ -21,6 +21,8 @@
 //                              (src/common/single_threaded_blas.cpp:24-36)
 //   * set_random_hpd<T>()      include/dlaf/util_matrix.h:161-189, :335-389, :410-453, :529-531
 //   * residual<T>()            miniapp/miniapp_cholesky.cpp:408-446 (max|A-LL^H| / max|A|, lower)
+//   * triangular_solver_local  include/dlaf/solver/triangular/impl.h:236-480 (the eight local loop nests), pinned to the
+//                              closed forms of test/include/dlaf_test/matrix/util_generic_blas.h:259-371
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -398,6 +400,66 @@ double residual(char uplo, long n, const T* a, long lda, const T* f, long ldf) {
   return max_d / max_a;
 }
 
+// ---- triangular solver --------------------------------------------------------------------------
+// Restatement of the reference's LOCAL tile loops Triangular<B,D,T>::call_{LLN,LLT,LUN,LUT,RLN,RLT,RUN,RUT}
+// (include/dlaf/solver/triangular/impl.h:236-480): per step one tile TRSM per tile of the k-th row (Left) / column
+// (Right) panel of B — with alpha applied there — and GEMM updates of the remaining tiles with beta = -1 / alpha
+// (impl.h:257, :287, ...). Tile operations: blas::trsm / blas::gemm (blas/tile.h:175-182, :238-245) = OpenBLAS here.
+// B is m x n in tiles mb x nb; A is square of order m (Left, tiles mb) or n (Right, tiles nb).
+template <class T>
+void triangular_solver_local(char side, char uplo, char op, char diag, T alpha, long m, long n, long mb, long nb,
+                             const T* a, long lda, T* b, long ldb) {
+  if (m == 0 || n == 0)
+    return;
+  const bool left = (side == 'L');
+  const bool lower = (uplo == 'L');
+  const bool notrans = (op == 'N');
+  const long mt = (m + mb - 1) / mb, nt = (n + nb - 1) / nb;
+  auto rows = [&](long i) { return static_cast<int>(std::min(mb, m - i * mb)); };
+  auto cols = [&](long j) { return static_cast<int>(std::min(nb, n - j * nb)); };
+  auto B = [&](long i, long j) { return b + i * mb + j * nb * ldb; };
+  const long ba = left ? mb : nb;
+  auto A = [&](long i, long j) { return a + i * ba + j * ba * lda; };
+  const T beta = T(-1) / alpha;
+  const int la = static_cast<int>(lda), lb = static_cast<int>(ldb);
+  // op(A) lower  <=>  (uplo == Lower) == (op == NoTrans)
+  const bool op_a_lower = (lower == notrans);
+  if (left) {
+    // op(A) X = alpha B: forward over the row panels when op(A) is lower (call_LLN / call_LUT), backward otherwise
+    const bool fwd = op_a_lower;
+    for (long s = 0; s < mt; ++s) {
+      const long k = fwd ? s : mt - 1 - s;
+      for (long j = 0; j < nt; ++j) {
+        trsm('L', uplo, op, diag, rows(k), cols(j), alpha, A(k, k), la, B(k, j), lb);
+        for (long i = fwd ? k + 1 : 0; i < (fwd ? mt : k); ++i) {
+          // op(A)(i,k): stored tile (i,k) for NoTrans, (k,i) otherwise
+          if (notrans)
+            gemm('N', 'N', rows(i), cols(j), rows(k), beta, A(i, k), la, B(k, j), lb, T(1), B(i, j), lb);
+          else
+            gemm(op, 'N', rows(i), cols(j), rows(k), beta, A(k, i), la, B(k, j), lb, T(1), B(i, j), lb);
+        }
+      }
+    }
+  }
+  else {
+    // X op(A) = alpha B: forward over the column panels when op(A) is upper (call_RUN / call_RLT), backward otherwise
+    const bool fwd = !op_a_lower;
+    for (long s = 0; s < nt; ++s) {
+      const long k = fwd ? s : nt - 1 - s;
+      for (long i = 0; i < mt; ++i) {
+        trsm('R', uplo, op, diag, rows(i), cols(k), alpha, A(k, k), la, B(i, k), lb);
+        for (long j = fwd ? k + 1 : 0; j < (fwd ? nt : k); ++j) {
+          // op(A)(k,j): stored tile (k,j) for NoTrans, (j,k) otherwise
+          if (notrans)
+            gemm('N', 'N', rows(i), cols(j), cols(k), beta, B(i, k), lb, A(k, j), la, T(1), B(i, j), lb);
+          else
+            gemm('N', op, rows(i), cols(j), cols(k), beta, B(i, k), lb, A(j, k), la, T(1), B(i, j), lb);
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 #define EXPORT_TYPE(sfx, T)                                                                      \
@@ -411,6 +473,13 @@ double residual(char uplo, long n, const T* a, long lda, const T* f, long ldf) {
     int info = potrf(uplo, static_cast<int>(n), static_cast<T*>(a), static_cast<int>(lda));      \
     scipy_openblas_set_num_threads(prev);                                                        \
     return info;                                                                                 \
+  }                                                                                              \
+  extern "C" void oracle_triangular_solver_##sfx(char side, char uplo, char op, char diag,       \
+                                                 const void* alpha, long m, long n, long mb,     \
+                                                 long nb, const void* a, long lda, void* b,      \
+                                                 long ldb) {                                     \
+    triangular_solver_local<T>(side, uplo, op, diag, *static_cast<const T*>(alpha), m, n, mb, nb, \
+                               static_cast<const T*>(a), lda, static_cast<T*>(b), ldb);          \
   }                                                                                              \
   extern "C" void oracle_set_random_hpd_##sfx(long n, long nb, void* a, long lda) {              \
     set_random_hpd<T>(n, nb, static_cast<T*>(a), lda);                                           \

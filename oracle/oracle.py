@@ -221,6 +221,89 @@ def check_near(expected: np.ndarray, value: np.ndarray, rel_err: float, abs_err:
                         f"abs {diff[idx]:.3e} > {abs_err:.3e}); {np.count_nonzero(~ok)} elements differ")
 
 
+# ---------------------------------------------------------------------------------------------
+# Triangular solver: the reference's local tile loops (oracle_triangular_solver_*) and its closed-form test systems
+# (test/include/dlaf_test/matrix/util_generic_blas.h:259-371), sizes / alpha / tolerance of
+# test/unit/solver/test_triangular.cpp:54-66, :100-101, :149.
+# ---------------------------------------------------------------------------------------------
+TRIANGULAR_TEST_SIZES = [(0, 0, 1, 1), (0, 2, 1, 2), (7, 0, 2, 1), (2, 2, 5, 5), (10, 10, 2, 3), (7, 7, 3, 2), (3, 2, 7, 7),
+                         (12, 3, 5, 5), (7, 6, 3, 2), (15, 7, 3, 5), (2, 3, 7, 7), (4, 13, 5, 5), (7, 8, 2, 9), (19, 25, 6, 5)]
+TRIANGULAR_TEST_ALPHA = complex(-1.2, 0.7)  # TypeUtilities<T>::element(-1.2, .7): the imaginary part is dropped for real T
+
+
+def triangular_solver(side: str, uplo: str, op: str, diag: str, alpha, a: np.ndarray, b: np.ndarray, mb: int, nb: int) -> None:
+    """In place on the Fortran-ordered b: op(A) X = alpha B (side 'L') or X op(A) = alpha B (side 'R')."""
+    _check_fortran(b)
+    m, n = b.shape
+    if m == 0 or n == 0:
+        return
+    _check_fortran(a)
+    f = getattr(lib(), f"oracle_triangular_solver_{type_char(b.dtype)}")
+    cc, cl, vp = ctypes.c_char, ctypes.c_long, ctypes.c_void_p
+    f.argtypes = [cc, cc, cc, cc, vp, cl, cl, cl, cl, vp, cl, vp, cl]
+    f.restype = None
+    if np.dtype(b.dtype).kind != "c" and op.upper() == "C":
+        op = "T"  # ConjTrans == Trans for real types (include/dlaf/gpu/blas/gpublas.h:107-112)
+    al = np.array([alpha], dtype=b.dtype)
+    f(side.upper().encode(), uplo.upper().encode(), op.upper().encode(), diag.upper().encode(), al.ctypes.data, m, n, mb, nb,
+      a.ctypes.data, max(1, a.strides[1] // a.itemsize), b.ctypes.data, max(1, b.strides[1] // b.itemsize))
+
+
+def _polar(r, theta, dtype):
+    return (r * np.exp(1j * theta)).astype(dtype) if np.dtype(dtype).kind == "c" else np.asarray(r).astype(dtype)
+
+
+def triangular_system(side: str, uplo: str, op: str, diag: str, alpha, m: int, n: int, dtype):
+    """(A, B, X): A as STORED (so that op(A) has the closed form below; unreferenced entries and a unit diagonal hold the
+    sentinel -9.9), B, and the exact solution X — getLeftTriangularSystem / getRightTriangularSystem of the reference.
+    `set(mat_a, el_op_a, op)` of the test stores A(i,j) = el_op_a(i,j) (NoTrans), el_op_a(j,i) (Trans) or its conjugate."""
+    dtype = np.dtype(dtype)
+    left = side.upper() == "L"
+    na = m if left else n
+    op_a_lower = (uplo.upper() == "L") == (op.upper() == "N")
+    i = np.arange(na, dtype=np.float64)[:, None]
+    k = np.arange(na, dtype=np.float64)[None, :]
+    if left:
+        opa = _polar((i + 1) / (k + 0.5), 2 * i - k, dtype)       # op(A)_ik
+    else:
+        opa = _polar((k + 1) / (i + 0.5), 2 * k - i, dtype)       # op(A)_kj with (row, col) = (i, k) here
+    unref = (i < k) if op_a_lower else (i > k)
+    if diag.upper() == "U":
+        unref = unref | (i == k)
+    opa = np.where(unref, np.asarray(SENTINEL).astype(dtype), opa)
+    if op.upper() == "N":
+        a = opa
+    elif op.upper() == "T":
+        a = opa.T
+    else:
+        a = opa.conj().T
+    r = np.arange(m, dtype=np.float64)[:, None]
+    c = np.arange(n, dtype=np.float64)[None, :]
+    al = np.asarray(alpha).astype(dtype)
+    if left:
+        x = _polar((r + 0.5) / (c + 2), r + c, dtype)
+        kk = (r + 1) if op_a_lower else (m - r)
+        gamma = _polar((r + 1) / (c + 2), 2 * r + c, dtype)
+    else:
+        x = _polar((c + 0.5) / (r + 2), r + c, dtype)
+        kk = (n - c) if op_a_lower else (c + 1)
+        gamma = _polar((c + 1) / (r + 2), r + 2 * c, dtype)
+    if diag.upper() == "U":
+        bmat = ((kk - 1) * gamma + x) / al
+    else:
+        bmat = kk * gamma / al
+    return np.asfortranarray(a.astype(dtype)), np.asfortranarray(np.broadcast_to(bmat, (m, n)).astype(dtype)), \
+        np.asfortranarray(np.broadcast_to(x, (m, n)).astype(dtype))
+
+
+def triangular_tolerance(m: int, dtype, distributed: bool = False) -> float:
+    """test_triangular.cpp:100-101 (local: 40 (m+1) error), :138-139 (distributed: 20 (m+1) error)."""
+    dtype = np.dtype(dtype)
+    eps = np.finfo(dtype.type(0).real.dtype).eps
+    err = (8 if dtype.kind == "c" else 2) * eps  # TypeUtilities<T>::error (util_types.h:40, :62)
+    return (20 if distributed else 40) * (m + 1) * err
+
+
 # Sizes of the reference's algorithm test (test/unit/factorization/test_cholesky.cpp:54-58): (m, mb)
 CHOLESKY_TEST_SIZES = [(0, 2), (5, 8), (34, 34), (4, 3), (16, 10), (34, 13), (32, 5)]
 
@@ -278,6 +361,22 @@ def scatter_block_cyclic(a: np.ndarray, nb: int, grid, src=(0, 0)):
             rows = [g for g in range(nt) if rank_global_tile(g, P, src[0]) == p]
             cols = [g for g in range(nt) if rank_global_tile(g, Q, src[1]) == q]
             ridx = np.concatenate([np.arange(g * nb, min(n, (g + 1) * nb)) for g in rows]) if rows else np.zeros(0, int)
+            cidx = np.concatenate([np.arange(g * nb, min(n, (g + 1) * nb)) for g in cols]) if cols else np.zeros(0, int)
+            out[(p, q)] = np.asfortranarray(a[np.ix_(ridx, cidx)])
+    return out
+
+
+def scatter_block_cyclic_rect(a: np.ndarray, mb: int, nb: int, grid, src=(0, 0)):
+    """Rectangular flavour (blocks mb x nb) for the right-hand sides of the triangular solver."""
+    P, Q = grid
+    m, n = a.shape
+    mt, nt = -(-m // mb), -(-n // nb)
+    out = {}
+    for p in range(P):
+        for q in range(Q):
+            rows = [g for g in range(mt) if rank_global_tile(g, P, src[0]) == p]
+            cols = [g for g in range(nt) if rank_global_tile(g, Q, src[1]) == q]
+            ridx = np.concatenate([np.arange(g * mb, min(m, (g + 1) * mb)) for g in rows]) if rows else np.zeros(0, int)
             cidx = np.concatenate([np.arange(g * nb, min(n, (g + 1) * nb)) for g in cols]) if cols else np.zeros(0, int)
             out[(p, q)] = np.asfortranarray(a[np.ix_(ridx, cidx)])
     return out

@@ -149,6 +149,63 @@ def main():
         info = pkg.cholesky_factorization(ctx, "L", loc, nb, n=n)
         if rank < P * Q and (want != 326 or info != want):
             failures.append(("info dense indefinite", info, want))
+    if a.mode == "gpu":
+        # ---- distributed triangular solver (test/unit/solver/test_triangular.cpp:106-140, :197-213): the reference's
+        # closed-form systems on the grid with a non-zero source rank, every side / uplo / op / diag combination
+        import itertools
+
+        tcases = [(10, 10, 2, 3), (15, 7, 3, 5), (19, 25, 6, 5), (7, 8, 2, 9)]
+        big = [(600, 400, 128, 64, "d"), (384, 512, 64, 128, "z"), (300, 260, 100, 50, "s")]
+        combos = list(itertools.product("LR", "LU", "NTC", "NU"))
+        for (m, n, mb, nb) in tcases:
+            for t in "sdcz":
+                dt = pkg.TYPES[t]
+                alpha = O.TRIANGULAR_TEST_ALPHA if np.dtype(dt).kind == "c" else O.TRIANGULAR_TEST_ALPHA.real
+                for side, uplo, op, diag in combos:
+                    A, B, X = O.triangular_system(side, uplo, op, diag, alpha, m, n, dt)
+                    ba = mb if side == "L" else nb
+                    if rank < P * Q:
+                        la = np.asfortranarray(O.scatter_block_cyclic(A, ba, (P, Q), src)[(myrow, mycol)])
+                        lb = np.asfortranarray(O.scatter_block_cyclic_rect(B, mb, nb, (P, Q), src)[(myrow, mycol)])
+                        lx = O.scatter_block_cyclic_rect(X, mb, nb, (P, Q), src)[(myrow, mycol)]
+                    else:
+                        la = lb = lx = np.zeros((1, 1), dtype=dt, order="F")
+                    if la.size == 0:
+                        la = np.zeros((max(1, la.shape[0]), max(1, la.shape[1])), dtype=dt, order="F")
+                    lbw = lb if lb.size else np.zeros((max(1, lb.shape[0]), max(1, lb.shape[1])), dtype=dt, order="F")
+                    pkg.triangular_solver(ctx, side, uplo, op, diag, alpha, la, lbw, mb, nb, m=m, n=n, isrc=src[0], jsrc=src[1])
+                    if rank < P * Q and lb.size:
+                        tol = O.triangular_tolerance(m, dt, distributed=True)
+                        ok, _, msg = O.check_near(lx, lbw, tol, tol)
+                        if not ok:
+                            failures.append(("trsm", t, side, uplo, op, diag, m, n, mb, nb, msg))
+        for (m, n, mb, nb, t) in big:
+            dt = pkg.TYPES[t]
+            rng = np.random.default_rng(17)
+            for side, uplo, op in [("L", "L", "N"), ("L", "L", "C"), ("R", "U", "N"), ("R", "L", "T"), ("L", "U", "T")]:
+                na, ba = (m, mb) if side == "L" else (n, nb)
+                spd = O.set_random_hermitian_positive_definite(na, ba, dt)
+                assert O.cholesky_local(uplo, spd, ba, 4) == 0
+                A = np.asfortranarray(np.tril(spd) if uplo == "L" else np.triu(spd))
+                B = rng.uniform(-1, 1, (m, n)).astype(dt)
+                B = np.asfortranarray(B)
+                ref = B.copy(order="F")
+                O.triangular_solver(side, uplo, op, "N", 1.0, A, ref, mb, nb)
+                if rank < P * Q:
+                    la = np.asfortranarray(O.scatter_block_cyclic(A, ba, (P, Q), src)[(myrow, mycol)])
+                    lb = np.asfortranarray(O.scatter_block_cyclic_rect(B, mb, nb, (P, Q), src)[(myrow, mycol)])
+                    lx = O.scatter_block_cyclic_rect(ref, mb, nb, (P, Q), src)[(myrow, mycol)]
+                else:
+                    la = lb = lx = np.zeros((1, 1), dtype=dt, order="F")
+                if la.size == 0:
+                    la = np.zeros((max(1, la.shape[0]), max(1, la.shape[1])), dtype=dt, order="F")
+                lbw = lb if lb.size else np.zeros((max(1, lb.shape[0]), max(1, lb.shape[1])), dtype=dt, order="F")
+                pkg.triangular_solver(ctx, side, uplo, op, "N", 1.0, la, lbw, mb, nb, m=m, n=n, isrc=src[0], jsrc=src[1])
+                if rank < P * Q and lb.size:
+                    tol = O.triangular_tolerance(max(m, n), dt, distributed=True) * max(1.0, float(np.abs(ref).max()))
+                    ok, _, msg = O.check_near(lx, lbw, tol, tol)
+                    if not ok:
+                        failures.append(("trsm big", t, side, uplo, op, m, n, mb, nb, msg))
     flag = torch.tensor([len(failures)], dtype=torch.int64, device="cuda" if a.mode == "gpu" else "cpu")
     dist.all_reduce(flag)
     if failures:

@@ -38,7 +38,7 @@ C_API_SYMBOLS = [
     "dlaf_b200_ozaki_pairs",
     "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops", "dlaf_b200_measure_int8_tensor_peak_tops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
-    *[f"dlaf_b200_triangular_solver_{t}" for t in "sdcz"], "dlaf_b200_last_solver_launch_count",
+    *[f"dlaf_b200_triangular_solver_{t}" for t in "sdcz"], "dlaf_b200_last_solver_launch_count", "dlaf_b200_last_solver_device_ms",
     "dlaf_b200_rank_global_tile", "dlaf_b200_local_tile_from_global_tile", "dlaf_b200_next_local_tile_from_global_tile",
     "dlaf_b200_global_tile_from_local_tile",
 ]
@@ -148,6 +148,8 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_wait.restype = ci
     L.dlaf_b200_last_solver_launch_count.argtypes = [ci]
     L.dlaf_b200_last_solver_launch_count.restype = ctypes.c_long
+    L.dlaf_b200_last_solver_device_ms.argtypes = [ci]
+    L.dlaf_b200_last_solver_device_ms.restype = ctypes.c_double
     L.dlaf_b200_guard_fallback_steps.argtypes = [ci]
     L.dlaf_b200_guard_fallback_steps.restype = ci
     L.dlaf_b200_ozaki_pairs.restype = ci
@@ -307,6 +309,10 @@ def triangular_solver(ctx: int, side: str, uplo: str, op: str, diag: str, alpha,
 
 def last_solver_launch_count(ctx: int) -> int:
     return lib().dlaf_b200_last_solver_launch_count(ctx)
+
+
+def last_solver_device_ms(ctx: int) -> float:
+    return lib().dlaf_b200_last_solver_device_ms(ctx)
 
 
 def guard_fallback_steps(ctx: int) -> int:

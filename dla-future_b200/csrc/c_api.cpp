@@ -89,6 +89,7 @@ struct GridCtx {
   cudaStream_t stream = nullptr;  // stream of the synchronous host API
   int* d_red = nullptr;           // info reduction buffer
   long last_solver_launches = 0;  // kernels launched by the last triangular solve
+  float last_solver_ms = 0.f;     // its device time (CUDA events around the device-resident part)
   ~GridCtx() {
     for (auto& s : slot)
       s.reset();
@@ -506,7 +507,16 @@ int triangular_solver_host(int ctx, char side, char uplo, char op, char diag, co
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dB, sizeof(D) * ldB, b, sizeof(D) * db.ld, sizeof(D) * lrb, lcb, cudaMemcpyHostToDevice, s));
   }
   const std::complex<double> al(*alpha);
+  cudaEvent_t e0, e1;
+  DLAF_CUDA_CHECK(cudaEventCreate(&e0));
+  DLAF_CUDA_CHECK(cudaEventCreate(&e1));
+  DLAF_CUDA_CHECK(cudaEventRecord(e0, s));
   c.last_solver_launches = triangular_solve_device<D>(p, al.real(), al.imag(), dA, ldA, dB, ldB, g.row_comm, g.col_comm, s);
+  DLAF_CUDA_CHECK(cudaEventRecord(e1, s));
+  DLAF_CUDA_CHECK(cudaEventSynchronize(e1));
+  DLAF_CUDA_CHECK(cudaEventElapsedTime(&c.last_solver_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   if (lrb > 0 && lcb > 0)
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(b, sizeof(D) * db.ld, dB, sizeof(D) * ldB, sizeof(D) * lrb, lcb, cudaMemcpyDeviceToHost, s));
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -721,6 +731,9 @@ long dlaf_b200_global_tile_from_local_tile(long local_tile, int grid_size, int r
 
 long dlaf_b200_last_solver_launch_count(int ctx) noexcept {
   return grid_from_context(ctx).last_solver_launches;
+}
+double dlaf_b200_last_solver_device_ms(int ctx) noexcept {
+  return grid_from_context(ctx).last_solver_ms;
 }
 
 int dlaf_b200_guard_fallback_steps(int ctx) noexcept {

@@ -1,12 +1,15 @@
 // See trsm_engine.h.
 #include "trsm_engine.h"
 
+#include <cstdlib>
+#include <string>
 #include <type_traits>
 #include <vector>
 
 #include "comm.h"
 #include "common.h"
 #include "distribution.h"
+#include "gemm_ozaki.h"
 
 namespace dlaf_b200 {
 
@@ -303,6 +306,22 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
     DLAF_CUDA_CHECK(cudaMalloc(&panelR, sizeof(T) * tsz * (ltrR > 0 ? ltrR : 1)));
   DLAF_CUDA_CHECK(cudaMalloc(&panelG, sizeof(T) * tsz * (ltcY > 0 ? ltcY : 1)));
 
+  // fp64: the per-step update runs on tcgen05 as exact int8 digit products (gemm_ozaki.h), like the POTRF trailing update —
+  // Y_k and the G tiles of the step are cut into digit planes first; same guard (a step whose operands span too many
+  // binades inside a row is updated by the native DMMA kernel). DLAF_B200_D_BULK=dmma keeps everything native.
+  bool use_oz = false;
+  OzakiSplit oz_a, oz_b;
+  int* oz_flag = nullptr;
+  if constexpr (std::is_same_v<T, double>) {
+    const char* e = std::getenv("DLAF_B200_D_BULK");
+    use_oz = (e == nullptr || std::string(e) == "ozaki") && nbp <= 512 && ltcY > 0 && nt > 1;
+    if (use_oz) {
+      oz_a.allocate(ldy, nbp);
+      oz_b.allocate(static_cast<long>(pattern_n && Pe == 1 ? (ltrR > 0 ? ltrR : 1) : ltcY) * nbp, nbp);
+      DLAF_CUDA_CHECK(cudaMalloc(&oz_flag, sizeof(int) * nt));
+      DLAF_CUDA_CHECK(cudaMemsetAsync(oz_flag, 0, sizeof(int) * nt, s));
+    }
+  }
   auto gemm = [&](const GemmArgsT<T>& g) {
     if (g.M <= 0 || g.N <= 0 || g.K <= 0)
       return;
@@ -487,7 +506,32 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
       u.mask = kMaskNone;
       u.nbp = nbp;
       u.P = u.Q = 1;
-      gemm(u);
+      bool done = false;
+      if constexpr (std::is_same_v<T, double>) {
+        if (use_oz) {
+          // digit planes of this step's operands: Y_k (plain column-major) and the G tiles (tile-contiguous)
+          int* flag = oz_flag + step;
+          oz_a.split(ya, ldy, ldy, s, 0, 0, flag);
+          const bool strided = (pattern_n && Pe == 1);
+          const long nb_rows = strided ? static_cast<long>(li1 - li0) * nbp : static_cast<long>(ncols) * nbp;
+          oz_b.split(strided ? panelR : gb, nbp, nb_rows, s, nbp, static_cast<long>(tsz), flag);
+          const long b_row = strided ? (static_cast<long>(lj0) * Qe + ecol - (forward ? k + 1 : 0)) * nbp : 0;
+          launch_gemm_ozaki_i8(u, oz_a, 0, oz_b, b_row, s, strided ? static_cast<long>(Qe) * nbp : 0, flag);
+          launch_gemm_nt_f64_if(u, flag, s);
+          launches += 4;
+          done = true;
+        }
+      }
+      if (!done)
+        gemm(u);
+    }
+  }
+  if constexpr (std::is_same_v<T, double>) {
+    if (use_oz) {
+      DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+      oz_a.release();
+      oz_b.release();
+      cudaFree(oz_flag);
     }
   }
   if (ltcY > 0) {

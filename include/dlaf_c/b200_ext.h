@@ -32,6 +32,9 @@ DLAF_EXTERN_C int dlaf_b200_triangular_solver_c(int ctx, char side, char uplo, c
 DLAF_EXTERN_C int dlaf_b200_triangular_solver_z(int ctx, char side, char uplo, char op, char diag, const dlaf_complex_z* alpha, const dlaf_complex_z* a, struct DLAF_descriptor desca, dlaf_complex_z* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
 /* Number of this library's kernel launches issued by the last triangular solve on ctx. */
 DLAF_EXTERN_C long dlaf_b200_last_solver_launch_count(int ctx) DLAF_NOEXCEPT;
+/* Device time [ms] of the last triangular solve on ctx (CUDA events around the device-resident part: layout conversion,
+ * diagonal-block inverses, the sweep; host <-> device copies excluded). */
+DLAF_EXTERN_C double dlaf_b200_last_solver_device_ms(int ctx) DLAF_NOEXCEPT;
 
 /* fp64 only. The trailing update runs as exact int8 digit products on tcgen05 (DLAF_B200_D_BULK=ozaki, default) with a
  * data-dependent guard: a step whose panel has a row spanning more than ~40 binades (an entry would keep fewer than

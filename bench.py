@@ -40,8 +40,10 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    p.add_argument("--n", type=int, default=32768, help="matrix size (BASELINE metric: 32768)")
-    p.add_argument("--nb", type=int, default=512, help="block size (BASELINE metric: 512)")
+    # (--matrix-size / --block-size are the miniapp's names; under torchrun use them: its own parser rejects "--n" as an
+    # ambiguous abbreviation of --nnodes / --nproc-per-node even after the script name)
+    p.add_argument("--n", "--matrix-size", dest="n", type=int, default=32768, help="matrix size (BASELINE metric: 32768)")
+    p.add_argument("--nb", "--block-size", dest="nb", type=int, default=512, help="block size (BASELINE metric: 512)")
     p.add_argument("--grid-rows", type=int, default=0)
     p.add_argument("--grid-cols", type=int, default=0)
     p.add_argument("--type", default="d", choices=["s", "d", "c", "z"], help="element type (BASELINE metric: d)")

@@ -12,6 +12,8 @@
 #pragma once
 
 #include <complex>
+#include <cstdio>
+#include <cstdlib>
 #include <type_traits>
 
 #include <dlaf/communication/communicator_grid.h>
@@ -48,7 +50,11 @@ void cholesky_factorization(comm::CommunicatorGrid& grid, const blas::Uplo uplo,
   static_assert(std::is_same_v<T, float> || std::is_same_v<T, double> || std::is_same_v<T, std::complex<float>> ||
                     std::is_same_v<T, std::complex<double>>,
                 "element types: float, double, std::complex<float>, std::complex<double>");
-  (void) grid;  // the matrix carries the context of the grid it was created on (checked to be the same)
+  // equal_process_grid(mat_a, grid) of the reference (cholesky.h:76): the matrix must have been created on this grid
+  if (grid.context() != mat_a.context()) {
+    std::fprintf(stderr, "[dlaf] cholesky_factorization: the matrix is not distributed on the given communicator grid\n");
+    std::abort();
+  }
   internal::call_device(mat_a.context(), internal::uplo_char(uplo), mat_a.ptr(), mat_a.descriptor(), mat_a.stream());
 }
 

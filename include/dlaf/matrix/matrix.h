@@ -34,8 +34,12 @@ public:
   // Distributed over `grid`, source rank (0, 0) (matrix.h:112-114); allocates the local part
   // (Device::CPU: pinned host memory, Device::GPU: device memory; ld = local rows rounded up to even).
   Matrix(GlobalElementSize size, TileElementSize block, comm::CommunicatorGrid& grid)
-      : size_(size), block_(block), ctx_(grid.context()), grid_size_(grid.size()) {
-    init_geometry(0, 0, 0);
+      : Matrix(size, block, grid, comm::Index2D(0, 0)) {}
+  // Same with an explicit source rank (the reference passes it through Distribution, matrix/distribution.h:115-160,
+  // as in test/unit/factorization/test_cholesky.cpp:85-88).
+  Matrix(GlobalElementSize size, TileElementSize block, comm::CommunicatorGrid& grid, comm::Index2D src_rank)
+      : size_(size), block_(block), ctx_(grid.context()), grid_size_(grid.size()), src_rank_(src_rank) {
+    init_geometry(static_cast<int>(src_rank.row()), static_cast<int>(src_rank.col()), 0);
     const std::size_t bytes = sizeof(T) * static_cast<std::size_t>(ld_) * (lcols_ > 0 ? lcols_ : 1);
     if (D == Device::GPU)
       internal::check(cudaMalloc(reinterpret_cast<void**>(&ptr_), bytes), "Matrix allocation");
@@ -47,7 +51,7 @@ public:
   // Wraps caller memory: local part at `ptr`, column-major with leading dimension `ld`.
   Matrix(GlobalElementSize size, TileElementSize block, comm::CommunicatorGrid& grid, comm::Index2D src_rank,
          T* ptr, SizeType ld)
-      : size_(size), block_(block), ctx_(grid.context()), grid_size_(grid.size()), ptr_(ptr) {
+      : size_(size), block_(block), ctx_(grid.context()), grid_size_(grid.size()), src_rank_(src_rank), ptr_(ptr) {
     init_geometry(static_cast<int>(src_rank.row()), static_cast<int>(src_rank.col()), ld);
     internal::check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "stream");
   }
@@ -71,6 +75,7 @@ public:
   TileElementSize block_size() const { return block_; }
   LocalElementSize localSize() const { return LocalElementSize(lrows_, lcols_); }
   comm::Size2D commGridSize() const { return grid_size_; }
+  comm::Index2D sourceRankIndex() const { return src_rank_; }
   T* ptr() { return ptr_; }
   const T* ptr() const { return ptr_; }
   SizeType ld() const { return ld_; }
@@ -97,6 +102,7 @@ private:
   TileElementSize block_;
   int ctx_;
   comm::Size2D grid_size_;
+  comm::Index2D src_rank_{0, 0};
   T* ptr_ = nullptr;
   SizeType ld_ = 1, lrows_ = 0, lcols_ = 0;
   DLAF_descriptor desc_{};
@@ -123,7 +129,8 @@ template <class T, Device Target, Device Source>
 class MatrixMirror {
 public:
   explicit MatrixMirror(Matrix<T, Source>& source, comm::CommunicatorGrid& grid)
-      : source_(source), twin_(source.size(), source.blockSize(), grid) {
+      : source_(source), twin_(source.size(), source.blockSize(), grid, source.sourceRankIndex()) {
+    // same distribution (grid, block size AND source rank) as the source: the local parts have identical shapes
     copy(source_, twin_);
   }
   ~MatrixMirror() {

@@ -39,6 +39,9 @@ C_API_SYMBOLS = [
     "dlaf_b200_set_profiling", "dlaf_b200_read_profile", "dlaf_b200_read_chain_profile", "dlaf_b200_measure_fp64_tensor_peak_tflops", "dlaf_b200_measure_int8_tensor_peak_tops",
     "dlaf_b200_local_rows", "dlaf_b200_local_cols",
     *[f"dlaf_b200_triangular_solver_{t}" for t in "sdcz"], "dlaf_b200_last_solver_launch_count", "dlaf_b200_last_solver_device_ms",
+    *[f"dlaf_inverse_from_cholesky_factor_{t}" for t in "sdcz"], *[f"dlaf_p{t}potri" for t in "sdcz"],
+    *[f"dlaf_b200_triangular_inverse_{t}" for t in "sdcz"], *[f"dlaf_b200_assemble_cholesky_inverse_{t}" for t in "sdcz"],
+    *[f"dlaf_b200_inverse_device_{t}" for t in "sdcz"], "dlaf_b200_last_inverse_guard_steps",
     "dlaf_b200_rank_global_tile", "dlaf_b200_local_tile_from_global_tile", "dlaf_b200_next_local_tile_from_global_tile",
     "dlaf_b200_global_tile_from_local_tile",
 ]
@@ -142,6 +145,21 @@ def lib() -> ctypes.CDLL:
         f = getattr(L, f"dlaf_b200_check_cholesky_device_{t}")
         f.argtypes = [ci, cc, vp, vp, DLAF_descriptor, vp]
         f.restype = ctypes.c_double
+        f = getattr(L, f"dlaf_inverse_from_cholesky_factor_{t}")
+        f.argtypes = [ci, cc, vp, DLAF_descriptor]
+        f.restype = ci
+        f = getattr(L, f"dlaf_p{t}potri")
+        f.argtypes = [cc, ci, vp, ci, ci, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+        f.restype = None
+        f = getattr(L, f"dlaf_b200_triangular_inverse_{t}")
+        f.argtypes = [ci, cc, cc, vp, DLAF_descriptor]
+        f.restype = ci
+        f = getattr(L, f"dlaf_b200_assemble_cholesky_inverse_{t}")
+        f.argtypes = [ci, cc, vp, DLAF_descriptor]
+        f.restype = ci
+        f = getattr(L, f"dlaf_b200_inverse_device_{t}")
+        f.argtypes = [ci, ci, cc, cc, vp, DLAF_descriptor, vp]
+        f.restype = ci
     L.dlaf_b200_grid_barrier.argtypes = [ci]
     L.dlaf_b200_grid_barrier.restype = None
     L.dlaf_b200_wait.argtypes = [ci, vp]
@@ -150,6 +168,8 @@ def lib() -> ctypes.CDLL:
     L.dlaf_b200_last_solver_launch_count.restype = ctypes.c_long
     L.dlaf_b200_last_solver_device_ms.argtypes = [ci]
     L.dlaf_b200_last_solver_device_ms.restype = ctypes.c_double
+    L.dlaf_b200_last_inverse_guard_steps.argtypes = [ci]
+    L.dlaf_b200_last_inverse_guard_steps.restype = ci
     L.dlaf_b200_guard_fallback_steps.argtypes = [ci]
     L.dlaf_b200_guard_fallback_steps.restype = ci
     L.dlaf_b200_ozaki_pairs.restype = ci
@@ -305,6 +325,52 @@ def triangular_solver(ctx: int, side: str, uplo: str, op: str, diag: str, alpha,
     al = np.array([alpha], dtype=b.dtype)
     f = getattr(lib(), f"dlaf_b200_triangular_solver_{type_char(b.dtype)}")
     f(ctx, side.encode(), uplo.encode(), op.encode(), diag.encode(), al.ctypes.data, a.ctypes.data, da, b.ctypes.data, db)
+
+
+def inverse_from_cholesky_factor(ctx: int, uplo: str, a: np.ndarray, nb: int, n: int | None = None, isrc: int = 0,
+                                 jsrc: int = 0) -> int:
+    """dlaf_inverse_from_cholesky_factor_{s,d,c,z}: `a` = this rank's HOST local part holding the Cholesky factor in the
+    `uplo` triangle, overwritten with the `uplo` triangle of inv(A)."""
+    n = a.shape[0] if n is None else n
+    d = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, _ld_of(a)))
+    return getattr(lib(), f"dlaf_inverse_from_cholesky_factor_{type_char(a.dtype)}")(ctx, uplo.encode(), a.ctypes.data, d)
+
+
+def ppotri(ctx: int, uplo: str, a: np.ndarray, nb: int, n: int | None = None, isrc: int = 0, jsrc: int = 0) -> int:
+    """dlaf_p{s,d,c,z}potri (ScaLAPACK-like descriptor; the context travels in desca[1])."""
+    n = a.shape[0] if n is None else n
+    desca = (ctypes.c_int * 9)(1, ctx, n, n, nb, nb, isrc, jsrc, max(1, _ld_of(a)))
+    info = ctypes.c_int(-1)
+    getattr(lib(), f"dlaf_p{type_char(a.dtype)}potri")(uplo.encode(), n, a.ctypes.data, 1, 1, desca, ctypes.byref(info))
+    return info.value
+
+
+def triangular_inverse(ctx: int, uplo: str, diag: str, a: np.ndarray, nb: int, n: int | None = None, isrc: int = 0,
+                       jsrc: int = 0) -> int:
+    """dlaf::triangular_inverse through the C ABI (HOST local part, in place)."""
+    n = a.shape[0] if n is None else n
+    d = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, _ld_of(a)))
+    return getattr(lib(), f"dlaf_b200_triangular_inverse_{type_char(a.dtype)}")(ctx, uplo.encode(), diag.encode(), a.ctypes.data, d)
+
+
+def assemble_cholesky_inverse(ctx: int, uplo: str, a: np.ndarray, nb: int, n: int | None = None, isrc: int = 0,
+                              jsrc: int = 0) -> int:
+    """Second half of inverse_from_cholesky_factor alone: T -> T^H T ('L') / T T^H ('U') (HOST local part, in place)."""
+    n = a.shape[0] if n is None else n
+    d = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, _ld_of(a)))
+    return getattr(lib(), f"dlaf_b200_assemble_cholesky_inverse_{type_char(a.dtype)}")(ctx, uplo.encode(), a.ctypes.data, d)
+
+
+def inverse_device(ctx: int, phases: int, uplo: str, diag: str, dev_ptr: int, dtype, n: int, nb: int, ld: int,
+                   stream: int = 0, isrc: int = 0, jsrc: int = 0) -> int:
+    """The inverse algorithms on a DEVICE local part (phases: 1 triangular inverse, 2 assemble, 3 both)."""
+    d = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, ld))
+    return getattr(lib(), f"dlaf_b200_inverse_device_{type_char(dtype)}")(ctx, phases, uplo.encode(), diag.encode(), dev_ptr, d,
+                                                                          stream)
+
+
+def last_inverse_guard_steps(ctx: int) -> int:
+    return lib().dlaf_b200_last_inverse_guard_steps(ctx)
 
 
 def last_solver_launch_count(ctx: int) -> int:

@@ -16,11 +16,13 @@
 #include <dlaf_c/factorization/cholesky.h>
 #include <dlaf_c/grid.h>
 #include <dlaf_c/init.h>
+#include <dlaf_c/inverse/cholesky.h>
 
 #include "comm.h"
 #include "common.h"
 #include "distribution.h"
 #include "engine.h"
+#include "inverse_engine.h"
 #include "trsm_engine.h"
 #include "util_matrix.h"
 
@@ -90,6 +92,7 @@ struct GridCtx {
   int* d_red = nullptr;           // info reduction buffer
   long last_solver_launches = 0;  // kernels launched by the last triangular solve
   float last_solver_ms = 0.f;     // its device time (CUDA events around the device-resident part)
+  int last_inverse_guard_steps = 0;  // fp64 steps of the last inverse that fell back to the native kernel
   ~GridCtx() {
     for (auto& s : slot)
       s.reset();
@@ -525,6 +528,90 @@ int triangular_solver_host(int ctx, char side, char uplo, char op, char diag, co
   return 0;
 }
 
+// dlaf::triangular_inverse / dlaf::inverse_from_cholesky_factor (include/dlaf/inverse/{triangular,cholesky}.h) on the DEVICE
+// copy of the local part (user layout): in place, collective over the grid of ctx, synchronous on `s`.
+template <class T>
+int inverse_on_device(int ctx, int phases, char uplo, char diag, T* a_dev, const DLAF_descriptor& d, cudaStream_t s) {
+  using D = devtype_t<T>;
+  ensure_device();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return 0;
+  const CommGrid& g = *c.grid;
+  DLAF_B200_ASSERT(uplo == 'L' || uplo == 'l' || uplo == 'U' || uplo == 'u', "uplo must be L or U");
+  DLAF_B200_ASSERT(diag == 'N' || diag == 'n' || diag == 'U' || diag == 'u', "diag must be N or U");
+  // preconditions of the reference (inverse/cholesky.h:39-41, :69-71; inverse/triangular.h:39-41, :66-68)
+  DLAF_B200_ASSERT(d.m == d.n && d.mb == d.nb, "the matrix must be square with square blocks");
+  DLAF_B200_ASSERT(d.i == 0 && d.j == 0, "sub-matrix offsets must be 0");
+  DLAF_B200_ASSERT(d.isrc >= 0 && d.isrc < g.P && d.jsrc >= 0 && d.jsrc < g.Q, "source rank");
+  InverseProblem p;
+  p.uplo = uplo;
+  p.diag = diag;
+  p.n = d.n;
+  p.nb = d.nb;
+  p.P = g.P;
+  p.Q = g.Q;
+  p.prow = (g.row - d.isrc + g.P) % g.P;
+  p.pcol = (g.col - d.jsrc + g.Q) % g.Q;
+  p.src_row = d.isrc;
+  p.src_col = d.jsrc;
+  const long lr = local_size_1d(d.n, d.nb, g.P, p.prow);
+  DLAF_B200_ASSERT(d.ld >= std::max<long>(1, lr), "leading dimension smaller than local rows");
+  cudaEvent_t e0, e1;
+  DLAF_CUDA_CHECK(cudaEventCreate(&e0));
+  DLAF_CUDA_CHECK(cudaEventCreate(&e1));
+  DLAF_CUDA_CHECK(cudaEventRecord(e0, s));
+  c.last_solver_launches = inverse_device<D>(p, phases, reinterpret_cast<D*>(a_dev), d.ld, g.row_comm, g.col_comm, s,
+                                             &c.last_inverse_guard_steps);
+  DLAF_CUDA_CHECK(cudaEventRecord(e1, s));
+  DLAF_CUDA_CHECK(cudaEventSynchronize(e1));
+  DLAF_CUDA_CHECK(cudaEventElapsedTime(&c.last_solver_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
+// ... on HOST local parts (the reference's MatrixMirror bracket, src/c_api/inverse/cholesky.h:40-59)
+template <class T>
+int inverse_host(int ctx, int phases, char uplo, char diag, T* a, const DLAF_descriptor& d) {
+  using D = devtype_t<T>;
+  ensure_device();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return 0;
+  const CommGrid& g = *c.grid;
+  DLAF_B200_ASSERT(d.isrc >= 0 && d.isrc < g.P && d.jsrc >= 0 && d.jsrc < g.Q, "source rank");
+  const int vrow = (g.row - d.isrc + g.P) % g.P, vcol = (g.col - d.jsrc + g.Q) % g.Q;
+  const long lr = local_size_1d(d.n, d.nb, g.P, vrow), lc = local_size_1d(d.n, d.nb, g.Q, vcol);
+  cudaStream_t s = ctx_stream(c);
+  D* dA = nullptr;
+  const long ldA = std::max<long>(lr, 1);
+  if (lr > 0 && lc > 0) {
+    DLAF_B200_ASSERT(d.ld >= lr, "leading dimension smaller than local rows");
+    DLAF_CUDA_CHECK(cudaMalloc(&dA, sizeof(D) * ldA * lc));
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dA, sizeof(D) * ldA, a, sizeof(D) * d.ld, sizeof(D) * lr, lc, cudaMemcpyHostToDevice, s));
+  }
+  DLAF_descriptor dd = d;
+  dd.ld = static_cast<int>(ldA);
+  inverse_on_device<T>(ctx, phases, uplo, diag, reinterpret_cast<T*>(dA), dd, s);
+  if (lr > 0 && lc > 0)
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(a, sizeof(D) * d.ld, dA, sizeof(D) * ldA, sizeof(D) * lr, lc, cudaMemcpyDeviceToHost, s));
+  DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(dA);
+  return 0;
+}
+
+template <class T>
+void pxpotri(char uplo, int n, T* a, int ia, int ja, const int desca[9], int* info) {
+  // src/c_api/inverse/cholesky.h:63-75
+  DLAF_B200_ASSERT(desca[0] == 1, "only dense descriptors (dtype 1)");
+  DLAF_B200_ASSERT(ia == 1 && ja == 1, "ia and ja must be 1");
+  const DLAF_descriptor d = make_dlaf_descriptor(n, n, ia, ja, desca);
+  const int r = inverse_host<T>(desca[1], kInverseFromCholeskyFactor, uplo, 'N', a, d);
+  if (info)
+    *info = r;
+}
+
 template <class T>
 void random_hpd(int ctx, T* a, const DLAF_descriptor& desc) {
   ensure_initialized();
@@ -693,6 +780,24 @@ struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int 
   double dlaf_b200_check_cholesky_device_##sfx(int ctx, char uplo, const T* a_dev, const T* f_dev,            \
                                                struct DLAF_descriptor d, void* stream) noexcept {             \
     return check_cholesky_device<T>(ctx, uplo, a_dev, f_dev, d, static_cast<cudaStream_t>(stream));           \
+  }                                                                                                           \
+  int dlaf_inverse_from_cholesky_factor_##sfx(const int ctx, const char uplo, T* a,                           \
+                                              const struct DLAF_descriptor d) noexcept {                      \
+    return inverse_host<T>(ctx, kInverseFromCholeskyFactor, uplo, 'N', a, d);                                 \
+  }                                                                                                           \
+  void dlaf_p##sfx##potri(const char uplo, const int n, T* a, const int ia, const int ja, const int desca[9], \
+                          int* info) noexcept {                                                               \
+    pxpotri<T>(uplo, n, a, ia, ja, desca, info);                                                              \
+  }                                                                                                           \
+  int dlaf_b200_triangular_inverse_##sfx(int ctx, char uplo, char diag, T* a, struct DLAF_descriptor d) noexcept { \
+    return inverse_host<T>(ctx, kTriangularInverse, uplo, diag, a, d);                                        \
+  }                                                                                                           \
+  int dlaf_b200_assemble_cholesky_inverse_##sfx(int ctx, char uplo, T* a, struct DLAF_descriptor d) noexcept { \
+    return inverse_host<T>(ctx, kAssembleFromInverseFactor, uplo, 'N', a, d);                                 \
+  }                                                                                                           \
+  int dlaf_b200_inverse_device_##sfx(int ctx, int phases, char uplo, char diag, T* a_dev,                     \
+                                     struct DLAF_descriptor d, void* stream) noexcept {                       \
+    return inverse_on_device<T>(ctx, phases, uplo, diag, a_dev, d, static_cast<cudaStream_t>(stream));        \
   }
 
 DLAF_B200_DEFINE(d, double)
@@ -741,6 +846,10 @@ int dlaf_b200_guard_fallback_steps(int ctx) noexcept {
   if (c.last_type < 0 || !c.slot[c.last_type])
     return -1;
   return c.slot[c.last_type]->guard_fallback_steps();
+}
+
+int dlaf_b200_last_inverse_guard_steps(int ctx) noexcept {
+  return grid_from_context(ctx).last_inverse_guard_steps;
 }
 
 int dlaf_b200_ozaki_pairs(void) noexcept {

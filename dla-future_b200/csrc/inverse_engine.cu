@@ -1,0 +1,463 @@
+// See inverse_engine.h.
+#include "inverse_engine.h"
+
+#include <cstdlib>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "comm.h"
+#include "common.h"
+#include "distribution.h"
+#include "gemm_ozaki.h"
+#include "gemm_tf32.h"
+#include "tri_kernels.cuh"
+
+namespace dlaf_b200 {
+
+namespace {
+
+using namespace trik;
+
+// Caller's local part <-> padded lower-triangular engine slab (tiles nbp x nbp, ld = lds), 32 x 32 elements per CTA,
+// blockIdx.z = local tile (la + lb * ltr). Engine tile (ga, gb) = (la * Pe + erow, lb * Qe + ecol), element (r, c):
+//   not transposed: user local element (la * nb + r, lb * nb + c)
+//   transposed    : conj of user local element (lb * nb + c, la * nb + r)        (uplo == 'U': the engine works on A^H)
+// LOAD : tiles above the diagonal are skipped (the slab is zero there); diagonal tiles get zeros in their upper half,
+//        an identity in the padding and ones on the diagonal for Diag::Unit; everything else outside the matrix is zero.
+// STORE: only elements of the referenced triangle inside the matrix are written (not the diagonal for Diag::Unit).
+template <class T, bool LOAD>
+__global__ void inv_convert_kernel(T* __restrict__ a, long lda, T* __restrict__ slab, long lds, long n, int nb, int nbp,
+                                   int Pe, int Qe, int erow, int ecol, int ltr, bool transposed, bool unit) {
+  __shared__ T t[32][33];
+  const int la = blockIdx.z % ltr, lb = blockIdx.z / ltr;
+  const long ga = static_cast<long>(la) * Pe + erow, gb = static_cast<long>(lb) * Qe + ecol;
+  if (ga < gb)
+    return;
+  const int rows = static_cast<int>(max(0L, min(static_cast<long>(nb), n - ga * nb)));
+  const int cols = static_cast<int>(max(0L, min(static_cast<long>(nb), n - gb * nb)));
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (ga == gb && r0 + 31 < c0)
+    return;  // block strictly above the diagonal of a diagonal tile: zero in the slab, never stored
+  T* stile = slab + static_cast<long>(la) * nbp + static_cast<long>(lb) * nbp * lds;
+  const long ur0 = transposed ? static_cast<long>(lb) * nb : static_cast<long>(la) * nb;  // user local offset of the tile
+  const long uc0 = transposed ? static_cast<long>(la) * nb : static_cast<long>(lb) * nb;
+  const int tx = threadIdx.x;
+  if (LOAD) {
+    // phase 1: user -> t, coalesced along the user's rows
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+      const int r = transposed ? r0 + k : r0 + tx, c = transposed ? c0 + tx : c0 + k;  // engine element read here
+      T v = make_real<T>(0);
+      if (r < rows && c < cols)
+        v = transposed ? conj_val(a[(ur0 + c) + (uc0 + r) * lda]) : a[(ur0 + r) + (uc0 + c) * lda];
+      t[k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+      const int r = r0 + tx, c = c0 + k;
+      T v = transposed ? t[tx][k] : t[k][tx];
+      if (ga == gb) {
+        if (r < c)
+          v = make_real<T>(0);
+        else if (r == c && (unit || r >= rows))
+          v = make_real<T>(1);
+      }
+      stile[r + static_cast<long>(c) * lds] = v;
+    }
+  }
+  else {
+    for (int k = threadIdx.y; k < 32; k += blockDim.y)
+      t[k][tx] = stile[(r0 + tx) + static_cast<long>(c0 + k) * lds];  // t[c - c0][r - r0]
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+      const int r = transposed ? r0 + k : r0 + tx, c = transposed ? c0 + tx : c0 + k;
+      const bool ref = (ga > gb) || (r > c) || (r == c && !unit);
+      if (r < rows && c < cols && ref) {
+        if (transposed)
+          a[(ur0 + c) + (uc0 + r) * lda] = conj_val(t[tx][k]);
+        else
+          a[(ur0 + r) + (uc0 + c) * lda] = t[k][tx];
+      }
+    }
+  }
+}
+
+// ntiles contiguous nbp x nbp tiles <- identity
+template <class T>
+__global__ void inv_identity_kernel(T* __restrict__ w, int nbp, long tile_stride) {
+  T* d = w + static_cast<long>(blockIdx.y) * tile_stride + static_cast<long>(blockIdx.x) * nbp;
+  for (int r = threadIdx.x; r < nbp; r += blockDim.x)
+    d[r] = make_real<T>(r == static_cast<int>(blockIdx.x) ? 1 : 0);
+}
+
+// One operand of a bulk update: `rows` rows x nbp columns, either plain column-major (tile_stride == 0, leading
+// dimension ld) or tile-contiguous (nbp x nbp tiles with leading dimension ld = nbp, tile_stride elements apart).
+template <class T>
+struct Operand {
+  const T* x;
+  long ld;
+  long rows;
+  long tile_stride;
+};
+
+// The one-launch-per-step update C = C + alpha A B^H on the engine of the element type: fp64 -> int8 digit planes on
+// tcgen05 + guarded native fallback, fp32 -> 3xTF32 on tcgen05, complex -> native kernels.
+template <class T>
+struct BulkUpdate {
+  bool oz = false, tf = false;
+  OzakiSplit oa, ob;
+  Tf32Split ta, tb;
+  int* flags = nullptr;
+  int nflags = 0, used = 0;
+
+  void init(long rows_a, long rows_b, int nbp, int nsteps, cudaStream_t s) {
+    if constexpr (std::is_same_v<T, double>) {
+      const char* e = std::getenv("DLAF_B200_D_BULK");
+      oz = (e == nullptr || std::string(e) == "ozaki") && nbp <= 512 && rows_a > 0 && rows_b > 0;
+      if (oz) {
+        oa.allocate(rows_a, nbp);
+        ob.allocate(rows_b, nbp);
+        nflags = nsteps;
+        DLAF_CUDA_CHECK(cudaMalloc(&flags, sizeof(int) * nflags));
+        DLAF_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * nflags, s));
+      }
+    }
+    if constexpr (std::is_same_v<T, float>) {
+      tf = std::getenv("DLAF_B200_S_SIMT") == nullptr && rows_a > 0 && rows_b > 0;
+      if (tf) {
+        ta.allocate(rows_a, nbp);
+        tb.allocate(rows_b, nbp);
+      }
+    }
+    (void) rows_a, (void) rows_b, (void) nbp, (void) nsteps, (void) s;
+  }
+
+  // g: C, ldc, M, N, K, alpha, mask geometry filled in; A / B described by the operands. same: B is the same panel as A.
+  long run(GemmArgsT<T> g, const Operand<T>& a, const Operand<T>& b, bool same, cudaStream_t s) {
+    if (g.M <= 0 || g.N <= 0)
+      return 0;
+    g.A = a.x;
+    g.lda = a.ld;
+    g.a_ts = a.tile_stride;
+    g.B = b.x;
+    g.ldb = b.ld;
+    g.b_ts = b.tile_stride;
+    g.beta = 1.0;
+    if constexpr (std::is_same_v<T, double>) {
+      if (oz) {
+        DLAF_B200_ASSERT(used < nflags, "guard flags exhausted");
+        int* flag = flags + used++;
+        oa.split(a.x, a.ld, a.rows, s, a.tile_stride ? g.nbp : 0, a.tile_stride, flag);
+        if (!same)
+          ob.split(b.x, b.ld, b.rows, s, b.tile_stride ? g.nbp : 0, b.tile_stride, flag);
+        launch_gemm_ozaki_i8(g, oa, 0, same ? oa : ob, 0, s, 0, flag);
+        launch_gemm_nt_f64_if(g, flag, s);
+        return same ? 3 : 4;
+      }
+    }
+    if constexpr (std::is_same_v<T, float>) {
+      if (tf) {
+        ta.split(a.x, a.ld, a.rows, s, a.tile_stride ? g.nbp : 0, a.tile_stride);
+        if (!same)
+          tb.split(b.x, b.ld, b.rows, s, b.tile_stride ? g.nbp : 0, b.tile_stride);
+        launch_gemm_tf32x3(g, ta, 0, same ? ta : tb, 0, s);
+        return same ? 2 : 3;
+      }
+    }
+    launch_gemm_nt<T>(g, s);
+    return 1;
+  }
+
+  // number of steps whose guard fired (synchronises the stream); releases everything
+  int finish(cudaStream_t s) {
+    int fired = 0;
+    if (oz) {
+      DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+      if (used > 0) {
+        std::vector<int> h(used);
+        DLAF_CUDA_CHECK(cudaMemcpy(h.data(), flags, sizeof(int) * used, cudaMemcpyDeviceToHost));
+        for (int v : h)
+          fired += (v != 0);
+      }
+      oa.release();
+      ob.release();
+      cudaFree(flags);
+    }
+    if (tf) {
+      DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+      ta.release();
+      tb.release();
+    }
+    return fired;
+  }
+};
+
+}  // namespace
+
+template <class T>
+long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, ncclComm_t row_comm, ncclComm_t col_comm,
+                    cudaStream_t s, int* guard_steps) {
+  using NT = NcclType<T>;
+  constexpr int G = Gran<T>::value;
+  long launches = 0;
+  if (guard_steps)
+    *guard_steps = 0;
+  const bool transposed = (p.uplo == 'U' || p.uplo == 'u');
+  DLAF_B200_ASSERT(transposed || p.uplo == 'L' || p.uplo == 'l', "uplo must be L or U");
+  const bool unit = (p.diag == 'U' || p.diag == 'u');
+  const bool do_trtri = (phases & kTriangularInverse) != 0, do_assemble = (phases & kAssembleFromInverseFactor) != 0;
+  DLAF_B200_ASSERT(!(unit && do_assemble), "the Cholesky factor has a non-unit diagonal");
+  if (p.n == 0)
+    return 0;
+  const int nbp = static_cast<int>(round_up(p.nb, G));
+  const int ns = nbp / G;
+  const int nt = ceil_div(p.n, p.nb);
+  const size_t tsz = static_cast<size_t>(nbp) * nbp, wsz = static_cast<size_t>(ns) * G * G;
+  // ---- engine grid: the lower-triangular problem; uplo == 'U' works on A^H with the grid roles swapped
+  const int Pe = transposed ? p.Q : p.P, Qe = transposed ? p.P : p.Q;
+  const int erow = transposed ? p.pcol : p.prow, ecol = transposed ? p.prow : p.pcol;
+  ncclComm_t e_row_comm = transposed ? col_comm : row_comm;  // ranks of my ENGINE row (size Qe)
+  ncclComm_t e_col_comm = transposed ? row_comm : col_comm;  // ranks of my ENGINE column (size Pe)
+  const int e_src_in_col = transposed ? p.src_col : p.src_row, e_src_in_row = transposed ? p.src_row : p.src_col;
+  auto col_rank = [&](int v_erow) { return (v_erow + e_src_in_col) % Pe; };
+  auto row_rank = [&](int v_ecol) { return (v_ecol + e_src_in_row) % Qe; };
+  DLAF_B200_ASSERT(Pe == 1 || e_col_comm != nullptr, "communicator required");
+  DLAF_B200_ASSERT(Qe == 1 || e_row_comm != nullptr, "communicator required");
+
+  const int ltr = cnt(nt, erow, Pe), ltc = cnt(nt, ecol, Qe);
+  const long lds = static_cast<long>(ltr > 0 ? ltr : 1) * nbp;
+  const bool have = ltr > 0 && ltc > 0;
+  T* slab = nullptr;
+  if (have) {
+    DLAF_CUDA_CHECK(cudaMalloc(&slab, sizeof(T) * lds * ltc * nbp));
+    DLAF_CUDA_CHECK(cudaMemsetAsync(slab, 0, sizeof(T) * lds * ltc * nbp, s));
+    dim3 grid(nbp / 32, nbp / 32, ltr * ltc), block(32, 8);
+    inv_convert_kernel<T, true><<<grid, block, 0, s>>>(a_user, lda, slab, lds, p.n, p.nb, nbp, Pe, Qe, erow, ecol, ltr, transposed,
+                                                       unit);
+    DLAF_CUDA_CHECK(cudaGetLastError());
+    ++launches;
+  }
+  auto tile = [&](long gi, long gj) { return slab + (gi / Pe) * nbp + (gj / Qe) * nbp * lds; };  // my stored tile (gi, gj)
+  auto pack = [&](const T* src, long ld_src, T* dst, long ld_dst, int ntiles, long src_stride, long dst_stride, bool tr, bool cj,
+                  bool neg) {
+    if (ntiles <= 0)
+      return;
+    dim3 grid(nbp / 32, nbp / 32, ntiles), block(32, 8);
+    trsm_pack_tile_kernel<T><<<grid, block, 0, s>>>(src, ld_src, dst, nbp, tr, cj, src_stride, dst_stride, ld_dst, neg);
+    DLAF_CUDA_CHECK(cudaGetLastError());
+    ++launches;
+  };
+  const bool is_complex = sizeof(T) == 2 * sizeof(base_t<T>);
+
+  // ---- workspaces
+  T *colp = nullptr, *panA = nullptr, *panB = nullptr, *dbuf = nullptr, *dloc = nullptr;
+  DLAF_CUDA_CHECK(cudaMalloc(&colp, sizeof(T) * static_cast<size_t>(ltr > 0 ? ltr : 1) * nbp * nbp));
+  DLAF_CUDA_CHECK(cudaMalloc(&panB, sizeof(T) * tsz * (ltc > 0 ? ltc : 1)));
+  if (do_assemble && Qe > 1)
+    DLAF_CUDA_CHECK(cudaMalloc(&panA, sizeof(T) * tsz * (ltr > 0 ? ltr : 1)));
+  DLAF_CUDA_CHECK(cudaMalloc(&dbuf, sizeof(T) * tsz));
+  BulkUpdate<T> bulk;
+  bulk.init(static_cast<long>(ltr) * nbp, static_cast<long>(ltc) * nbp, nbp, 2 * nt, s);
+
+  // =================================================================================================================
+  // (1) W = L^-1
+  if (do_trtri) {
+    // my diagonal tiles: [L_kk packed | inverted G-blocks | Wh_k = L_kk^-H], all up front (off the critical path)
+    std::vector<int> my_diag;
+    for (int k = 0; k < nt; ++k)
+      if (k % Pe == erow && k % Qe == ecol)
+        my_diag.push_back(k);
+    const size_t dsz = 2 * tsz + wsz;
+    if (!my_diag.empty()) {
+      DLAF_CUDA_CHECK(cudaMalloc(&dloc, sizeof(T) * dsz * my_diag.size()));
+      for (size_t i = 0; i < my_diag.size(); ++i)
+        pack(tile(my_diag[i], my_diag[i]), lds, dloc + dsz * i, nbp, 1, 0, 0, false, false, false);
+      static bool configured = false;
+      if (!configured) {
+        DLAF_CUDA_CHECK(cudaFuncSetAttribute(trsm_trtri_blocks_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(sizeof(T) * G * (G + 1))));
+        configured = true;
+      }
+      dim3 gridw(ns, static_cast<unsigned>(my_diag.size()));
+      trsm_trtri_blocks_kernel<T, G><<<gridw, G, sizeof(T) * G * (G + 1), s>>>(dloc, static_cast<long>(dsz), nbp, dloc + tsz,
+                                                                              static_cast<long>(dsz), true);
+      DLAF_CUDA_CHECK(cudaGetLastError());
+      dim3 gridi(nbp, static_cast<unsigned>(my_diag.size()));
+      inv_identity_kernel<T><<<gridi, 128, 0, s>>>(dloc + tsz + wsz, nbp, static_cast<long>(dsz));
+      DLAF_CUDA_CHECK(cudaGetLastError());
+      launches += 2;
+      for (size_t i = 0; i < my_diag.size(); ++i)  // I L_kk^-H by the panel substitution
+        launches += solve_rows_against_tile<T>(dloc + dsz * i + tsz + wsz, nbp, nbp, dloc + dsz * i, nbp, dloc + dsz * i + tsz, ns,
+                                               true, s);
+    }
+    for (int k = nt - 1; k >= 0; --k) {
+      const int owner_r = k % Pe, owner_c = k % Qe;
+      const bool in_col = (ecol == owner_c), in_row = (erow == owner_r);
+      const int li_k = cnt(k, erow, Pe), li_k1 = cnt(k + 1, erow, Pe);  // my first local row tile with global index >= k, > k
+      const int ncols = cnt(k, ecol, Qe);                                // my local block columns left of k
+      const long mk = static_cast<long>(ltr - li_k) * nbp;               // rows of the extended column panel on this rank
+      const long vrows = static_cast<long>(ltr - li_k1) * nbp;           // of which strictly below row k
+      if (in_col) {  // (a rank of this column without local rows still takes part in the broadcast)
+        const T* whk = nullptr;
+        if (in_row) {
+          size_t idx = 0;
+          while (my_diag[idx] != k)
+            ++idx;
+          whk = dloc + dsz * idx + tsz + wsz;
+        }
+        if (k < nt - 1 && Pe > 1) {
+          DLAF_NCCL_CHECK(ncclBroadcast(in_row ? whk : dbuf, dbuf, tsz * NT::mult, NT::value, col_rank(owner_r), e_col_comm, s));
+          whk = dbuf;
+        }
+        const long lck = k / Qe;
+        if (vrows > 0) {
+          // column panel: W(i,k) = -A(i,k) L_kk^-1 = -A(i,k) Wh_k^H, into the compact panel, then back into the matrix
+          GemmArgsT<T> g{};
+          g.A = slab + static_cast<long>(li_k1) * nbp + lck * nbp * lds;
+          g.lda = lds;
+          g.B = whk;
+          g.ldb = nbp;
+          g.C = colp + (li_k1 - li_k) * static_cast<long>(nbp);
+          g.ldc = mk;
+          g.M = static_cast<int>(vrows);
+          g.N = nbp;
+          g.K = nbp;
+          g.alpha = -1.0;
+          g.beta = 0.0;
+          g.mask = kMaskNone;
+          g.nbp = nbp;
+          g.P = g.Q = 1;
+          launch_gemm_nt<T>(g, s);
+          ++launches;
+          DLAF_CUDA_CHECK(cudaMemcpy2DAsync(slab + static_cast<long>(li_k1) * nbp + lck * nbp * lds, sizeof(T) * lds, g.C,
+                                            sizeof(T) * mk, sizeof(T) * vrows, nbp, cudaMemcpyDeviceToDevice, s));
+        }
+        if (in_row) {
+          // W_kk = Wh_k^H: first tile of the extended panel and the final diagonal tile
+          size_t idx = 0;
+          while (my_diag[idx] != k)
+            ++idx;
+          pack(dloc + dsz * idx + tsz + wsz, nbp, colp, mk, 1, 0, 0, true, is_complex, false);
+          DLAF_CUDA_CHECK(cudaMemcpy2DAsync(tile(k, k), sizeof(T) * lds, colp, sizeof(T) * mk, sizeof(T) * nbp, nbp,
+                                            cudaMemcpyDeviceToDevice, s));
+        }
+      }
+      if (k == 0)
+        break;
+      // extended column panel along the process rows
+      if (Qe > 1 && mk > 0)
+        DLAF_NCCL_CHECK(ncclBroadcast(colp, colp, static_cast<size_t>(mk) * nbp * NT::mult, NT::value, row_rank(owner_c), e_row_comm, s));
+      // row k: B(j) = -L(k,j)^H packed, row k zeroed, down the process columns
+      if (ncols > 0) {
+        if (in_row && have) {
+          pack(slab + static_cast<long>(k / Pe) * nbp, lds, panB, nbp, ncols, static_cast<long>(nbp) * lds, static_cast<long>(tsz),
+               true, is_complex, true);
+          DLAF_CUDA_CHECK(cudaMemset2DAsync(slab + static_cast<long>(k / Pe) * nbp, sizeof(T) * lds, 0, sizeof(T) * nbp,
+                                            static_cast<size_t>(ncols) * nbp, s));
+        }
+        if (Pe > 1)
+          DLAF_NCCL_CHECK(ncclBroadcast(panB, panB, tsz * ncols * NT::mult, NT::value, col_rank(owner_r), e_col_comm, s));
+      }
+      // trailing update + row panel: C(i >= k, j < k) -= V B^H
+      if (mk > 0 && ncols > 0) {
+        GemmArgsT<T> g{};
+        g.C = slab + static_cast<long>(li_k) * nbp;
+        g.ldc = lds;
+        g.M = static_cast<int>(mk);
+        g.N = ncols * nbp;
+        g.K = nbp;
+        g.alpha = -1.0;
+        g.mask = kMaskNone;
+        g.nbp = nbp;
+        g.P = g.Q = 1;
+        launches += bulk.run(g, Operand<T>{colp, mk, mk, 0}, Operand<T>{panB, nbp, static_cast<long>(ncols) * nbp, static_cast<long>(tsz)},
+                             false, s);
+      }
+    }
+  }
+
+  // =================================================================================================================
+  // (2) A^-1 = W^H W (lower triangle)
+  if (do_assemble) {
+    for (int k = 0; k < nt; ++k) {
+      const int owner_r = k % Pe;
+      const bool in_row = (erow == owner_r);
+      const int ncols = cnt(k + 1, ecol, Qe), nrows = cnt(k + 1, erow, Pe);
+      // P(j) = W(k,j)^H for my block columns j <= k, row k zeroed, down the process columns
+      if (ncols > 0) {
+        if (in_row && have) {
+          pack(slab + static_cast<long>(k / Pe) * nbp, lds, panB, nbp, ncols, static_cast<long>(nbp) * lds, static_cast<long>(tsz),
+               true, is_complex, false);
+          DLAF_CUDA_CHECK(cudaMemset2DAsync(slab + static_cast<long>(k / Pe) * nbp, sizeof(T) * lds, 0, sizeof(T) * nbp,
+                                            static_cast<size_t>(ncols) * nbp, s));
+        }
+        if (Pe > 1)
+          DLAF_NCCL_CHECK(ncclBroadcast(panB, panB, tsz * ncols * NT::mult, NT::value, col_rank(owner_r), e_col_comm, s));
+      }
+      // P(i) for my block rows i <= k: from the rank of my process row that sits in process column i % Qe
+      Operand<T> opa{};
+      if (Qe > 1) {
+        if (nrows > 0) {
+          DLAF_NCCL_CHECK(ncclGroupStart());
+          for (int li = 0; li < nrows; ++li) {
+            const long i = static_cast<long>(li) * Pe + erow;
+            const int root_v = static_cast<int>(i % Qe);
+            T* recv = panA + tsz * li;
+            const T* send = (root_v == ecol) ? panB + tsz * (i / Qe) : recv;
+            DLAF_NCCL_CHECK(ncclBroadcast(send, recv, tsz * NT::mult, NT::value, row_rank(root_v), e_row_comm, s));
+          }
+          DLAF_NCCL_CHECK(ncclGroupEnd());
+        }
+        opa = Operand<T>{panA, nbp, static_cast<long>(nrows) * nbp, static_cast<long>(tsz)};
+      }
+      else {
+        // one process column: every tile of row k is already here; my block rows are every Pe-th of them
+        opa = Operand<T>{panB + tsz * erow, nbp, static_cast<long>(nrows) * nbp, static_cast<long>(tsz) * Pe};
+      }
+      if (nrows > 0 && ncols > 0) {
+        GemmArgsT<T> g{};
+        g.C = slab;
+        g.ldc = lds;
+        g.M = nrows * nbp;
+        g.N = ncols * nbp;
+        g.K = nbp;
+        g.alpha = 1.0;
+        g.mask = kMaskLower;
+        g.nbp = nbp;
+        g.P = Pe;
+        g.Q = Qe;
+        g.prow = erow;
+        g.pcol = ecol;
+        launches += bulk.run(g, opa, Operand<T>{panB, nbp, static_cast<long>(ncols) * nbp, static_cast<long>(tsz)}, Pe * Qe == 1, s);
+      }
+    }
+  }
+
+  if (have) {
+    dim3 grid(nbp / 32, nbp / 32, ltr * ltc), block(32, 8);
+    inv_convert_kernel<T, false><<<grid, block, 0, s>>>(a_user, lda, slab, lds, p.n, p.nb, nbp, Pe, Qe, erow, ecol, ltr,
+                                                        transposed, unit);
+    DLAF_CUDA_CHECK(cudaGetLastError());
+    ++launches;
+  }
+  const int fired = bulk.finish(s);
+  if (guard_steps)
+    *guard_steps = fired;
+  DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(slab);
+  cudaFree(colp);
+  cudaFree(panA);
+  cudaFree(panB);
+  cudaFree(dbuf);
+  cudaFree(dloc);
+  return launches;
+}
+
+#define INST(T) \
+  template long inverse_device<T>(const InverseProblem&, int, T*, long, ncclComm_t, ncclComm_t, cudaStream_t, int*);
+INST(float)
+INST(double)
+INST(float2)
+INST(double2)
+
+}  // namespace dlaf_b200

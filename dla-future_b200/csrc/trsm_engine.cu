@@ -10,23 +10,13 @@
 #include "common.h"
 #include "distribution.h"
 #include "gemm_ozaki.h"
+#include "tri_kernels.cuh"
 
 namespace dlaf_b200 {
 
 namespace {
 
-template <class T>
-__device__ __forceinline__ T cj_if(T v, bool cj) {
-  return cj ? conj_val(v) : v;
-}
-__device__ __forceinline__ float scale_c(float v, double re, double) { return static_cast<float>(v * re); }
-__device__ __forceinline__ double scale_c(double v, double re, double) { return v * re; }
-__device__ __forceinline__ float2 scale_c(float2 v, double re, double im) {
-  return make_float2(static_cast<float>(v.x * re - v.y * im), static_cast<float>(v.x * im + v.y * re));
-}
-__device__ __forceinline__ double2 scale_c(double2 v, double re, double im) {
-  return make_double2(v.x * re - v.y * im, v.x * im + v.y * re);
-}
+using namespace trik;
 
 // Caller's local part of the triangular matrix -> padded tiles (nbp x nbp, ld = ltr * nbp): only the referenced triangle
 // is taken (the other one may hold anything), diagonal tiles get zeros in their unreferenced half, the padding of
@@ -92,111 +82,6 @@ __global__ void trsm_convert_y_kernel(T* __restrict__ b, long ldb, long lrb, lon
   }
 }
 
-// one padded tile of the stored matrix -> contiguous nbp x nbp tile of G (optionally transposed and / or conjugated)
-template <class T>
-__global__ void trsm_pack_tile_kernel(const T* __restrict__ src, long lds, T* __restrict__ dst, int nbp, bool tr, bool cj,
-                                      long src_tile_stride, long dst_tile_stride) {
-  __shared__ T t[32][33];
-  const T* s = src + static_cast<long>(blockIdx.z) * src_tile_stride;
-  T* d = dst + static_cast<long>(blockIdx.z) * dst_tile_stride;
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int k = threadIdx.y; k < 32; k += blockDim.y)
-    t[k][threadIdx.x] = cj_if(s[(r0 + threadIdx.x) + static_cast<long>(c0 + k) * lds], cj);  // t[col][row]
-  __syncthreads();
-  if (!tr) {
-    for (int k = threadIdx.y; k < 32; k += blockDim.y)
-      d[(r0 + threadIdx.x) + static_cast<long>(c0 + k) * nbp] = t[k][threadIdx.x];
-  }
-  else {
-    for (int k = threadIdx.y; k < 32; k += blockDim.y)
-      d[(c0 + threadIdx.x) + static_cast<long>(r0 + k) * nbp] = t[threadIdx.x][k];  // G(c, r) = A(r, c)
-  }
-}
-
-// W_j = inverse of the j-th GB x GB diagonal block of the packed triangular tile Gkk (lower or upper), GB columns in
-// parallel, each by substitution on the block held in shared memory (one CTA per block; off the critical path: all
-// diagonal tiles of a solve are inverted in one launch before the sweep starts).
-template <class T, int GB>
-__global__ void trsm_trtri_blocks_kernel(const T* __restrict__ g, long tile_stride, int nbp, T* __restrict__ w,
-                                         long w_tile_stride, bool lower) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* L = reinterpret_cast<T*>(smem_raw);  // GB x (GB + 1), column-major
-  constexpr int LD = GB + 1;
-  const int j = blockIdx.x, kt = blockIdx.y;
-  const T* blk = g + kt * tile_stride + static_cast<long>(j) * GB * (1 + nbp);
-  T* out = w + kt * w_tile_stride + static_cast<long>(j) * GB * GB;
-  for (int idx = threadIdx.x; idx < GB * GB; idx += blockDim.x)
-    L[(idx % GB) + (idx / GB) * LD] = blk[(idx % GB) + static_cast<long>(idx / GB) * nbp];
-  __syncthreads();
-  const int c = threadIdx.x;  // column of the inverse
-  if (c >= GB)
-    return;
-  using R = base_t<T>;
-  auto recip = [](T v) {
-    if constexpr (std::is_same_v<T, float> || std::is_same_v<T, double>) {
-      return static_cast<T>(R(1) / v);
-    }
-    else {
-      const R d = v.x * v.x + v.y * v.y;
-      T r;
-      r.x = v.x / d;
-      r.y = -v.y / d;
-      return r;
-    }
-  };
-  auto mul = [](T a, T b) {
-    if constexpr (std::is_same_v<T, float> || std::is_same_v<T, double>) {
-      return static_cast<T>(a * b);
-    }
-    else {
-      T r;
-      r.x = a.x * b.x - a.y * b.y;
-      r.y = a.x * b.y + a.y * b.x;
-      return r;
-    }
-  };
-  auto sub = [](T a, T b) {
-    if constexpr (std::is_same_v<T, float> || std::is_same_v<T, double>) {
-      return static_cast<T>(a - b);
-    }
-    else {
-      T r;
-      r.x = a.x - b.x;
-      r.y = a.y - b.y;
-      return r;
-    }
-  };
-  // the column under construction lives in (L1-resident) local memory; written out once at the end
-  T x[GB];
-  for (int i = 0; i < GB; ++i)
-    x[i] = make_real<T>(0);
-  if (lower) {
-    x[c] = recip(L[c + c * LD]);
-    for (int i = c + 1; i < GB; ++i) {
-      T sum = make_real<T>(0);
-      for (int k = c; k < i; ++k)
-        sum = sub(sum, mul(L[i + k * LD], x[k]));
-      x[i] = mul(sum, recip(L[i + i * LD]));
-    }
-  }
-  else {
-    x[c] = recip(L[c + c * LD]);
-    for (int i = c - 1; i >= 0; --i) {
-      T sum = make_real<T>(0);
-      for (int k = i + 1; k <= c; ++k)
-        sum = sub(sum, mul(L[i + k * LD], x[k]));
-      x[i] = mul(sum, recip(L[i + i * LD]));
-    }
-  }
-  T* o = out + static_cast<long>(c) * GB;
-  for (int i = 0; i < GB; ++i)
-    o[i] = x[i];
-}
-
-inline int cnt(long g_end, int v, int grid) {  // tiles of virtual rank v with global index < g_end
-  return static_cast<int>(next_local_tile_from_global_tile(g_end, grid, v, 0));
-}
-
 }  // namespace
 
 template <class T>
@@ -256,7 +141,7 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
     if (ntiles <= 0)
       return;
     dim3 grid(nbp / 32, nbp / 32, ntiles), block(32, 8);
-    trsm_pack_tile_kernel<T><<<grid, block, 0, s>>>(src, lds, dst, nbp, tr, cj, src_stride, dst_stride);
+    trsm_pack_tile_kernel<T><<<grid, block, 0, s>>>(src, lds, dst, nbp, tr, cj, src_stride, dst_stride, nbp, false);
     DLAF_CUDA_CHECK(cudaGetLastError());
     ++launches;
   };
@@ -328,62 +213,9 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
     launch_gemm_nt<T>(g, s);
     ++launches;
   };
-  // Y_k <- Y_k Gkk^-H by block substitution over the GB-blocks of the tile: forward for a lower tile, backward for an upper
+  // Y_k <- Y_k Gkk^-H by block substitution over the GB-blocks of the tile (tri_kernels.cuh)
   auto solve_tile = [&](T* yk, const T* gkk, const T* w) {
-    if constexpr (std::is_same_v<T, double>) {
-      if (g_lower) {  // the fused one-launch kernel of the POTRF panel (gemm_dmma.cuh)
-        TrsmFusedArgs fa{};
-        fa.B = yk;
-        fa.ldb = ldy;
-        fa.T = gkk;
-        fa.ldt = nbp;
-        fa.W = w;
-        fa.ns = ns;
-        launch_trsm_fused_f64(fa, static_cast<int>(ldy), s);
-        ++launches;
-        return;
-      }
-    }
-    for (int jj = 0; jj < ns; ++jj) {
-      const int j = g_lower ? jj : ns - 1 - jj;
-      T* yj = yk + static_cast<long>(j) * G * ldy;
-      const int kdone = g_lower ? j * G : (ns - 1 - j) * G;  // columns of Y_k already final
-      if (kdone > 0) {
-        const long c0 = g_lower ? 0 : static_cast<long>(j + 1) * G;
-        GemmArgsT<T> u{};
-        u.A = yk + c0 * ldy;
-        u.lda = ldy;
-        u.B = gkk + static_cast<long>(j) * G + c0 * nbp;  // row block j of G, the finished columns
-        u.ldb = nbp;
-        u.C = yj;
-        u.ldc = ldy;
-        u.M = static_cast<int>(ldy);
-        u.N = G;
-        u.K = kdone;
-        u.alpha = -1.0;
-        u.beta = 1.0;
-        u.mask = kMaskNone;
-        u.nbp = 1 << 30;
-        u.P = u.Q = 1;
-        gemm(u);
-      }
-      GemmArgsT<T> m{};
-      m.A = yj;
-      m.lda = ldy;
-      m.B = w + static_cast<long>(j) * G * G;
-      m.ldb = G;
-      m.C = yj;  // in place: Y_j <- Y_j inv(G_jj)^H
-      m.ldc = ldy;
-      m.M = static_cast<int>(ldy);
-      m.N = G;
-      m.K = G;
-      m.alpha = 1.0;
-      m.beta = 0.0;
-      m.mask = kMaskNone;
-      m.nbp = 1 << 30;
-      m.P = m.Q = 1;
-      gemm(m);
-    }
+    launches += solve_rows_against_tile<T>(yk, ldy, ldy, gkk, nbp, w, ns, g_lower, s);
   };
 
   // ---- the sweep

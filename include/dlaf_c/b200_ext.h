@@ -30,9 +30,31 @@ DLAF_EXTERN_C int dlaf_b200_triangular_solver_s(int ctx, char side, char uplo, c
 DLAF_EXTERN_C int dlaf_b200_triangular_solver_d(int ctx, char side, char uplo, char op, char diag, const double* alpha, const double* a, struct DLAF_descriptor desca, double* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
 DLAF_EXTERN_C int dlaf_b200_triangular_solver_c(int ctx, char side, char uplo, char op, char diag, const dlaf_complex_c* alpha, const dlaf_complex_c* a, struct DLAF_descriptor desca, dlaf_complex_c* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
 DLAF_EXTERN_C int dlaf_b200_triangular_solver_z(int ctx, char side, char uplo, char op, char diag, const dlaf_complex_z* alpha, const dlaf_complex_z* a, struct DLAF_descriptor desca, dlaf_complex_z* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
-/* Number of this library's kernel launches issued by the last triangular solve on ctx. */
+/* dlaf::triangular_inverse (include/dlaf/inverse/triangular.h:38-76; the reference has no C entry for it): the `uplo`
+ * triangle of the HOST local part a (diag 'U': its diagonal is assumed to be 1 and is neither read nor written) is
+ * overwritten with the inverse of that triangular matrix. Collective over the grid of ctx, synchronous. Returns 0. */
+DLAF_EXTERN_C int dlaf_b200_triangular_inverse_s(int ctx, char uplo, char diag, float* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_triangular_inverse_d(int ctx, char uplo, char diag, double* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_triangular_inverse_c(int ctx, char uplo, char diag, dlaf_complex_c* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_triangular_inverse_z(int ctx, char uplo, char diag, dlaf_complex_z* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+/* Second half of dlaf_inverse_from_cholesky_factor_* alone (AssembleCholeskyInverse, inverse/cholesky/impl.h:180-540):
+ * the triangular matrix T in the `uplo` triangle is overwritten with the `uplo` triangle of T^H T ('L') / T T^H ('U'). */
+DLAF_EXTERN_C int dlaf_b200_assemble_cholesky_inverse_s(int ctx, char uplo, float* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_assemble_cholesky_inverse_d(int ctx, char uplo, double* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_assemble_cholesky_inverse_c(int ctx, char uplo, dlaf_complex_c* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_assemble_cholesky_inverse_z(int ctx, char uplo, dlaf_complex_z* a, struct DLAF_descriptor desc) DLAF_NOEXCEPT;
+/* The same algorithms on the DEVICE copy of the local part (the C++ surface's Backend::GPU / Device::GPU flavour):
+ * phases = 1 triangular inverse, 2 assemble, 3 both (= inverse from the Cholesky factor). Synchronous on cuda_stream. */
+DLAF_EXTERN_C int dlaf_b200_inverse_device_s(int ctx, int phases, char uplo, char diag, float* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_inverse_device_d(int ctx, int phases, char uplo, char diag, double* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_inverse_device_c(int ctx, int phases, char uplo, char diag, dlaf_complex_c* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_inverse_device_z(int ctx, int phases, char uplo, char diag, dlaf_complex_z* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
+/* fp64: number of steps of the last inverse on ctx whose update ran on the native fp64 kernel because the int8 digit
+ * guard fired (see dlaf_b200_guard_fallback_steps). */
+DLAF_EXTERN_C int dlaf_b200_last_inverse_guard_steps(int ctx) DLAF_NOEXCEPT;
+/* Number of this library's kernel launches issued by the last triangular solve / inverse on ctx. */
 DLAF_EXTERN_C long dlaf_b200_last_solver_launch_count(int ctx) DLAF_NOEXCEPT;
-/* Device time [ms] of the last triangular solve on ctx (CUDA events around the device-resident part: layout conversion,
+/* Device time [ms] of the last triangular solve / inverse on ctx (CUDA events around the device-resident part: layout conversion,
  * diagonal-block inverses, the sweep; host <-> device copies excluded). */
 DLAF_EXTERN_C double dlaf_b200_last_solver_device_ms(int ctx) DLAF_NOEXCEPT;
 

@@ -23,6 +23,11 @@
 //   * residual<T>()            miniapp/miniapp_cholesky.cpp:408-446 (max|A-LL^H| / max|A|, lower)
 //   * triangular_solver_local  include/dlaf/solver/triangular/impl.h:236-480 (the eight local loop nests), pinned to the
 //                              closed forms of test/include/dlaf_test/matrix/util_generic_blas.h:259-371
+//   * triangular_inverse_local include/dlaf/inverse/triangular/impl.h:183-229 (call_L) and :367-413 (call_U), tile ops
+//                              :47-110 / :112-170; pinned to test/include/dlaf_test/matrix/util_generic_lapack.h:261-327
+//   * assemble_cholesky_inverse_local  include/dlaf/inverse/cholesky/impl.h:180-224 (call_L) and :361-405 (call_U), tile
+//                              ops :46-108 / :110-172; pinned to util_generic_lapack.h:165-196 and, chained after the
+//                              triangular inverse (include/dlaf/inverse/cholesky.h:38-52), to :212-247
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -49,7 +54,11 @@ char* scipy_openblas_get_config(void);
   void scipy_##p##trsm_(const char*, const char*, const char*, const char*, const int*,          \
                         const int*, const T*, const T*, const int*, T*, const int*);             \
   void scipy_##p##gemm_(const char*, const char*, const int*, const int*, const int*, const T*,  \
-                        const T*, const int*, const T*, const int*, const T*, T*, const int*);
+                        const T*, const int*, const T*, const int*, const T*, T*, const int*);     \
+  void scipy_##p##trmm_(const char*, const char*, const char*, const char*, const int*,          \
+                        const int*, const T*, const T*, const int*, T*, const int*);             \
+  void scipy_##p##trtri_(const char*, const char*, const int*, T*, const int*, int*);            \
+  void scipy_##p##lauum_(const char*, const int*, T*, const int*, int*);
 DECL_REAL(s, float)
 DECL_REAL(d, double)
 DECL_REAL(c, std::complex<float>)
@@ -460,6 +469,99 @@ void triangular_solver_local(char side, char uplo, char op, char diag, T alpha, 
   }
 }
 
+
+#define WRAP_INV(p, T)                                                                                        \
+  inline void trmm(char side, char uplo, char op, char diag, int m, int n, T alpha, const T* a, int lda, T* b, \
+                   int ldb) {                                                                                 \
+    scipy_##p##trmm_(&side, &uplo, &op, &diag, &m, &n, &alpha, a, &lda, b, &ldb);                             \
+  }                                                                                                           \
+  inline int trtri(char uplo, char diag, int n, T* a, int lda) {                                              \
+    int info = 0;                                                                                             \
+    scipy_##p##trtri_(&uplo, &diag, &n, a, &lda, &info);                                                      \
+    return info;                                                                                              \
+  }                                                                                                           \
+  inline int lauum(char uplo, int n, T* a, int lda) {                                                         \
+    int info = 0;                                                                                             \
+    scipy_##p##lauum_(&uplo, &n, a, &lda, &info);                                                             \
+    return info;                                                                                              \
+  }
+WRAP_INV(s, float)
+WRAP_INV(d, double)
+WRAP_INV(c, std::complex<float>)
+WRAP_INV(z, std::complex<double>)
+
+// ---- inverse ------------------------------------------------------------------------------------
+// Restatement of Triangular<B,D,T>::call_L / call_U (LOCAL), include/dlaf/inverse/triangular/impl.h:183-229, :367-413:
+// k from the last tile to the first; column (L) / row (U) panel tile TRSM with alpha = -1 against the still original
+// diagonal tile, GEMM of the trailing tiles, row (L) / column (U) panel TRSM with alpha = 1, tile trtri last.
+template <class T>
+void triangular_inverse_local(char uplo, char diag, long n, long nb, T* a, long lda) {
+  if (n == 0)
+    return;
+  const long nt = (n + nb - 1) / nb;
+  auto sz = [&](long i) { return static_cast<int>(std::min(nb, n - i * nb)); };
+  auto A = [&](long i, long j) { return a + i * nb + j * nb * lda; };
+  const int la = static_cast<int>(lda);
+  for (long k = nt - 1; k >= 0; --k) {
+    if (uplo == 'L') {
+      for (long i = k + 1; i < nt; ++i) {
+        trsm('R', 'L', 'N', diag, sz(i), sz(k), T(-1), A(k, k), la, A(i, k), la);  // impl.h:78-90
+        for (long j = 0; j < k; ++j)
+          gemm('N', 'N', sz(i), sz(j), sz(k), T(1), A(i, k), la, A(k, j), la, T(1), A(i, j), la);  // :92-109
+      }
+      for (long j = 0; j < k; ++j)
+        trsm('L', 'L', 'N', diag, sz(k), sz(j), T(1), A(k, k), la, A(k, j), la);  // :64-76
+      trtri('L', diag, sz(k), A(k, k), la);
+    }
+    else {
+      for (long j = k + 1; j < nt; ++j) {
+        trsm('L', 'U', 'N', diag, sz(k), sz(j), T(-1), A(k, k), la, A(k, j), la);  // impl.h:143-155
+        for (long i = 0; i < k; ++i)
+          gemm('N', 'N', sz(i), sz(j), sz(k), T(1), A(i, k), la, A(k, j), la, T(1), A(i, j), la);
+      }
+      for (long i = 0; i < k; ++i)
+        trsm('R', 'U', 'N', diag, sz(i), sz(k), T(1), A(k, k), la, A(i, k), la);  // :129-141
+      trtri('U', diag, sz(k), A(k, k), la);
+    }
+  }
+}
+
+// Restatement of AssembleCholeskyInverse<B,D,T>::call_L / call_U (LOCAL), include/dlaf/inverse/cholesky/impl.h:180-224,
+// :361-405: k ascending; GEMM / HERK of the leading tiles with row (L) / column (U) k, TRMM of that panel with the
+// diagonal tile, tile lauum last.
+template <class T>
+void assemble_cholesky_inverse_local(char uplo, long n, long nb, T* a, long lda) {
+  if (n == 0)
+    return;
+  using R = BaseT<T>;
+  const long nt = (n + nb - 1) / nb;
+  auto sz = [&](long i) { return static_cast<int>(std::min(nb, n - i * nb)); };
+  auto A = [&](long i, long j) { return a + i * nb + j * nb * lda; };
+  const int la = static_cast<int>(lda);
+  for (long k = 0; k < nt; ++k) {
+    if (uplo == 'L') {
+      for (long i = 0; i < k; ++i) {
+        for (long j = 0; j < i; ++j)
+          gemm('C', 'N', sz(i), sz(j), sz(k), T(1), A(k, i), la, A(k, j), la, T(1), A(i, j), la);  // impl.h:96-108
+        herk('L', 'C', sz(i), sz(k), R(1), A(k, i), la, R(1), A(i, i), la);                        // :83-94
+      }
+      for (long j = 0; j < k; ++j)
+        trmm('L', 'L', 'C', 'N', sz(k), sz(j), T(1), A(k, k), la, A(k, j), la);  // :69-81
+      lauum('L', sz(k), A(k, k), la);
+    }
+    else {
+      for (long j = 0; j < k; ++j) {
+        for (long i = 0; i < j; ++i)
+          gemm('N', 'C', sz(i), sz(j), sz(k), T(1), A(i, k), la, A(j, k), la, T(1), A(i, j), la);  // impl.h:158-170
+        herk('U', 'N', sz(j), sz(k), R(1), A(j, k), la, R(1), A(j, j), la);                        // :145-156
+      }
+      for (long i = 0; i < k; ++i)
+        trmm('R', 'U', 'C', 'N', sz(i), sz(k), T(1), A(k, k), la, A(i, k), la);  // :131-143
+      lauum('U', sz(k), A(k, k), la);
+    }
+  }
+}
+
 }  // namespace
 
 #define EXPORT_TYPE(sfx, T)                                                                      \
@@ -480,6 +582,19 @@ void triangular_solver_local(char side, char uplo, char op, char diag, T alpha, 
                                                  long ldb) {                                     \
     triangular_solver_local<T>(side, uplo, op, diag, *static_cast<const T*>(alpha), m, n, mb, nb, \
                                static_cast<const T*>(a), lda, static_cast<T*>(b), ldb);          \
+  }                                                                                              \
+  extern "C" void oracle_triangular_inverse_##sfx(char uplo, char diag, long n, long nb, void* a, \
+                                                  long lda) {                                    \
+    triangular_inverse_local<T>(uplo, diag, n, nb, static_cast<T*>(a), lda);                     \
+  }                                                                                              \
+  extern "C" void oracle_assemble_cholesky_inverse_##sfx(char uplo, long n, long nb, void* a,    \
+                                                         long lda) {                             \
+    assemble_cholesky_inverse_local<T>(uplo, n, nb, static_cast<T*>(a), lda);                    \
+  }                                                                                              \
+  extern "C" void oracle_inverse_from_cholesky_factor_##sfx(char uplo, long n, long nb, void* a, \
+                                                            long lda) {                          \
+    triangular_inverse_local<T>(uplo, 'N', n, nb, static_cast<T*>(a), lda);                      \
+    assemble_cholesky_inverse_local<T>(uplo, n, nb, static_cast<T*>(a), lda);                    \
   }                                                                                              \
   extern "C" void oracle_set_random_hpd_##sfx(long n, long nb, void* a, long lda) {              \
     set_random_hpd<T>(n, nb, static_cast<T*>(a), lda);                                           \

@@ -304,6 +304,99 @@ def triangular_tolerance(m: int, dtype, distributed: bool = False) -> float:
     return (20 if distributed else 40) * (m + 1) * err
 
 
+# ---------------------------------------------------------------------------------------------
+# Inverse: the reference's local tile loops (oracle_triangular_inverse_*, oracle_assemble_cholesky_inverse_*,
+# oracle_inverse_from_cholesky_factor_*) and the closed forms of its tests
+# (test/include/dlaf_test/matrix/util_generic_lapack.h:165-196, :212-247, :261-327), sizes and tolerance of
+# test/unit/inverse/test_triangular_inverse.cpp:54-58, :75-76 and test_inverse_from_cholesky_factor.cpp:53-57, :74-75.
+# ---------------------------------------------------------------------------------------------
+INVERSE_TEST_SIZES = [(0, 2), (5, 8), (34, 34), (4, 3), (16, 10), (34, 13), (32, 5)]  # (m, mb)
+
+
+def _inverse_call(name: str, a: np.ndarray, nb: int, *chars) -> None:
+    _check_fortran(a)
+    n = a.shape[0]
+    assert a.shape == (n, n)
+    if n == 0:
+        return
+    f = getattr(lib(), f"{name}_{type_char(a.dtype)}")
+    cc, cl, vp = ctypes.c_char, ctypes.c_long, ctypes.c_void_p
+    f.argtypes = [cc] * len(chars) + [cl, cl, vp, cl]
+    f.restype = None
+    f(*[c.upper().encode() for c in chars], n, nb, a.ctypes.data, max(1, a.strides[1] // a.itemsize))
+
+
+def triangular_inverse(uplo: str, diag: str, a: np.ndarray, nb: int) -> None:
+    """In place: the `uplo` triangle of the Fortran-ordered a <- inverse of that triangular matrix."""
+    _inverse_call("oracle_triangular_inverse", a, nb, uplo, diag)
+
+
+def assemble_cholesky_inverse(uplo: str, a: np.ndarray, nb: int) -> None:
+    """In place: triangular T in the `uplo` triangle <- `uplo` triangle of T^H T ('L') / T T^H ('U')."""
+    _inverse_call("oracle_assemble_cholesky_inverse", a, nb, uplo)
+
+
+def inverse_from_cholesky_factor(uplo: str, a: np.ndarray, nb: int) -> None:
+    """In place: Cholesky factor in the `uplo` triangle <- `uplo` triangle of inv(A)."""
+    _inverse_call("oracle_inverse_from_cholesky_factor", a, nb, uplo)
+
+
+def _ij(n: int):
+    return np.arange(n, dtype=np.float64)[:, None], np.arange(n, dtype=np.float64)[None, :]
+
+
+def _unref(uplo: str, i, j, with_diag: bool = False):
+    u = (i < j) if uplo.upper() == "L" else (i > j)
+    return (u | (i == j)) if with_diag else u
+
+
+def _finish(x, unref, dtype):
+    return np.asfortranarray(np.where(unref, np.asarray(SENTINEL).astype(dtype), x.astype(dtype)))
+
+
+def triangular_inverse_setters(uplo: str, diag: str, n: int, dtype):
+    """(A, inv(A)) of get_triangular_inverse_setters (util_generic_lapack.h:261-327); unreferenced entries (and the
+    diagonal for Diag::Unit) hold the sentinel in both."""
+    dtype = np.dtype(dtype)
+    i, j = _ij(n)
+    unit = diag.upper() == "U"
+    unref = _unref(uplo, i, j, unit)
+    scale, dval, oval = (1.0, 1.0, 0.5) if unit else (4.0, 0.25, 0.125)
+    a = _polar(scale * np.exp2(-np.abs(i - j)), -i + j, dtype)
+    off = -_polar(np.full((n, n), oval), -i + j, dtype)
+    res = np.where(i == j, np.asarray(dval).astype(dtype), np.where(np.abs(i - j) == 1, off, np.asarray(0).astype(dtype)))
+    return _finish(a, unref, dtype), _finish(res, unref, dtype)
+
+
+def assemble_cholesky_inverse_setters(uplo: str, n: int, dtype):
+    """(T, A) of get_assemble_cholesky_inverse_setters (util_generic_lapack.h:165-196): A = T^H T (Lower) / T T^H (Upper)."""
+    dtype = np.dtype(dtype)
+    i, j = _ij(n)
+    unref = _unref(uplo, i, j)
+    t = _polar(np.exp2(-np.abs(i - j)), -i + j, dtype)
+    ri, rj = n - 1 - i, n - 1 - j
+    a = _polar(np.exp2(-(ri + rj)) / 3 * (np.exp2(2 * (np.minimum(ri, rj) + 1)) - 1), ri - rj, dtype)
+    return _finish(t, unref, dtype), _finish(a, unref, dtype)
+
+
+def inverse_cholesky_factor_setters(uplo: str, n: int, dtype):
+    """(T, A) of get_inverse_cholesky_factor_setters (util_generic_lapack.h:212-247): T the Cholesky factor (bidiagonal),
+    A = inv(T^H) inv(T) (Lower) / inv(T) inv(T^H) (Upper)."""
+    dtype = np.dtype(dtype)
+    i, j = _ij(n)
+    unref = _unref(uplo, i, j)
+    off = -_polar(np.full((n, n), 0.5), -i + j, dtype)
+    t = np.where(i == j, np.asarray(1).astype(dtype), np.where(np.abs(i - j) == 1, off, np.asarray(0).astype(dtype)))
+    ri, rj = n - 1 - i, n - 1 - j
+    a = _polar(np.exp2(-(ri + rj)) / 3 * (np.exp2(2 * (np.minimum(ri, rj) + 1)) - 1), ri - rj, dtype)
+    return _finish(t, unref, dtype), _finish(a, unref, dtype)
+
+
+def inverse_tolerance(m: int, dtype) -> float:
+    """4 (m + 1) error, relative and absolute (test_triangular_inverse.cpp:75-76, test_inverse_from_cholesky_factor.cpp:74-75)."""
+    return 4 * (m + 1) * type_error(dtype)
+
+
 # Sizes of the reference's algorithm test (test/unit/factorization/test_cholesky.cpp:54-58): (m, mb)
 CHOLESKY_TEST_SIZES = [(0, 2), (5, 8), (34, 34), (4, 3), (16, 10), (34, 13), (32, 5)]
 

@@ -206,6 +206,66 @@ def main():
                     ok, _, msg = O.check_near(lx, lbw, tol, tol)
                     if not ok:
                         failures.append(("trsm big", t, side, uplo, op, m, n, mb, nb, msg))
+    if a.mode == "gpu":
+        # ---- distributed inverse (test/unit/inverse/test_triangular_inverse.cpp:78-99, test_inverse_from_cholesky_factor.cpp:
+        # 77-98): the reference's closed forms on the grid with a non-zero source rank, then a random Cholesky factor vs the oracle
+        def local_of(full, nb_, dt_):
+            if rank < P * Q:
+                loc = np.asfortranarray(O.scatter_block_cyclic(full, nb_, (P, Q), src)[(myrow, mycol)])
+            else:
+                loc = np.zeros((1, 1), dtype=dt_, order="F")
+            work = loc if loc.size else np.zeros((max(1, loc.shape[0]), max(1, loc.shape[1])), dtype=dt_, order="F")
+            return loc, work
+
+        for (m, mb) in [(16, 10), (34, 13), (32, 5), (4, 3)]:
+            for t in "sdcz":
+                dt = pkg.TYPES[t]
+                tol = O.inverse_tolerance(m, dt)
+                for uplo in "LU":
+                    for diag in "UN":
+                        A, R = O.triangular_inverse_setters(uplo, diag, m, dt)
+                        loc, work = local_of(A, mb, dt)
+                        pkg.triangular_inverse(ctx, uplo, diag, work, mb, n=m, isrc=src[0], jsrc=src[1])
+                        if rank < P * Q and loc.size:
+                            ok, _, msg = O.check_near(O.scatter_block_cyclic(R, mb, (P, Q), src)[(myrow, mycol)], work, tol, tol)
+                            if not ok:
+                                failures.append(("trtri", t, uplo, diag, m, mb, msg))
+                    T0, R = O.inverse_cholesky_factor_setters(uplo, m, dt)
+                    loc, work = local_of(T0, mb, dt)
+                    pkg.inverse_from_cholesky_factor(ctx, uplo, work, mb, n=m, isrc=src[0], jsrc=src[1])
+                    if rank < P * Q and loc.size:
+                        ok, _, msg = O.check_near(O.scatter_block_cyclic(R, mb, (P, Q), src)[(myrow, mycol)], work, tol, tol)
+                        if not ok:
+                            failures.append(("potri", t, uplo, m, mb, msg))
+                    T0, R = O.assemble_cholesky_inverse_setters(uplo, m, dt)
+                    loc, work = local_of(T0, mb, dt)
+                    pkg.assemble_cholesky_inverse(ctx, uplo, work, mb, n=m, isrc=src[0], jsrc=src[1])
+                    if rank < P * Q and loc.size:
+                        ok, _, msg = O.check_near(O.scatter_block_cyclic(R, mb, (P, Q), src)[(myrow, mycol)], work, tol, tol)
+                        if not ok:
+                            failures.append(("lauum", t, uplo, m, mb, msg))
+        for (m, mb, t) in [(1536, 256, "d"), (1100, 200, "d"), (768, 128, "z"), (1024, 256, "s")]:
+            dt = pkg.TYPES[t]
+            for uplo in "LU":
+                spd = O.set_random_hermitian_positive_definite(m, mb, dt)
+                fac = spd.copy(order="F")
+                assert O.cholesky_local(uplo, fac, mb, 4) == 0
+                tri = np.tril if uplo == "L" else np.triu
+                sent = np.full((m, m), -9.9)
+                fac = np.asfortranarray(tri(fac) + (np.triu(sent, 1) if uplo == "L" else np.tril(sent, -1)).astype(dt))
+                ref = fac.copy(order="F")
+                O.inverse_from_cholesky_factor(uplo, ref, mb)
+                loc, work = local_of(fac, mb, dt)
+                pkg.ppotri(ctx, uplo, work, mb, n=m, isrc=src[0], jsrc=src[1])
+                if rank < P * Q and loc.size:
+                    scale = float(np.abs(tri(ref)).max())
+                    tol = O.inverse_tolerance(m, dt)
+                    lref = O.scatter_block_cyclic(ref, mb, (P, Q), src)[(myrow, mycol)]
+                    # sentinels are compared unscaled (they must be bit-identical), the inverse relative to its largest entry
+                    lsent = O.scatter_block_cyclic(np.asfortranarray(~np.isclose(ref.real, -9.9)), mb, (P, Q), src)[(myrow, mycol)]
+                    ok, _, msg = O.check_near(np.where(lsent, lref / scale, lref), np.where(lsent, work / scale, work), tol, tol)
+                    if not ok:
+                        failures.append(("potri big", t, uplo, m, mb, msg))
     flag = torch.tensor([len(failures)], dtype=torch.int64, device="cuda" if a.mode == "gpu" else "cpu")
     dist.all_reduce(flag)
     if failures:

@@ -7,7 +7,7 @@ CSRC      := dla-future_b200/csrc
 LIBDIR    := dla-future_b200/lib
 LIB       := $(LIBDIR)/libdlaf_b200.so
 
-CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/gemm_zdmma.o build/gemm_tf32_tcgen05.o build/gemm_ozaki_i8.o build/potrf_tile.o build/potrf_tile_cluster.o build/layout.o build/engine.o build/sm_partition.o build/peak.o build/engine_check.o build/trsm_engine.o build/inverse_engine.o
+CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/gemm_zdmma.o build/gemm_tf32_tcgen05.o build/gemm_ozaki_i8.o build/potrf_tile.o build/potrf_tile_cluster.o build/layout.o build/engine.o build/sm_partition.o build/peak.o build/engine_check.o build/trsm_engine.o build/inverse_engine.o build/hegst_engine.o
 CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
 OBJS     := $(CU_OBJS) $(CPP_OBJS)
 HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h) $(wildcard include/dlaf_c/inverse/*.h)

@@ -42,6 +42,7 @@ C_API_SYMBOLS = [
     *[f"dlaf_inverse_from_cholesky_factor_{t}" for t in "sdcz"], *[f"dlaf_p{t}potri" for t in "sdcz"],
     *[f"dlaf_b200_triangular_inverse_{t}" for t in "sdcz"], *[f"dlaf_b200_assemble_cholesky_inverse_{t}" for t in "sdcz"],
     *[f"dlaf_b200_inverse_device_{t}" for t in "sdcz"], "dlaf_b200_last_inverse_guard_steps",
+    *[f"dlaf_b200_generalized_to_standard_{t}" for t in "sdcz"], *[f"dlaf_b200_generalized_to_standard_device_{t}" for t in "sdcz"],
     "dlaf_b200_rank_global_tile", "dlaf_b200_local_tile_from_global_tile", "dlaf_b200_next_local_tile_from_global_tile",
     "dlaf_b200_global_tile_from_local_tile",
 ]
@@ -159,6 +160,12 @@ def lib() -> ctypes.CDLL:
         f.restype = ci
         f = getattr(L, f"dlaf_b200_inverse_device_{t}")
         f.argtypes = [ci, ci, cc, cc, vp, DLAF_descriptor, vp]
+        f.restype = ci
+        f = getattr(L, f"dlaf_b200_generalized_to_standard_{t}")
+        f.argtypes = [ci, cc, vp, DLAF_descriptor, vp, DLAF_descriptor]
+        f.restype = ci
+        f = getattr(L, f"dlaf_b200_generalized_to_standard_device_{t}")
+        f.argtypes = [ci, cc, vp, DLAF_descriptor, vp, DLAF_descriptor, vp]
         f.restype = ci
     L.dlaf_b200_grid_barrier.argtypes = [ci]
     L.dlaf_b200_grid_barrier.restype = None
@@ -367,6 +374,24 @@ def inverse_device(ctx: int, phases: int, uplo: str, diag: str, dev_ptr: int, dt
     d = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, ld))
     return getattr(lib(), f"dlaf_b200_inverse_device_{type_char(dtype)}")(ctx, phases, uplo.encode(), diag.encode(), dev_ptr, d,
                                                                           stream)
+
+
+def generalized_to_standard(ctx: int, uplo: str, a: np.ndarray, b: np.ndarray, nb: int, n: int | None = None, isrc: int = 0,
+                            jsrc: int = 0) -> int:
+    """dlaf::eigensolver::internal::generalized_to_standard through the C ABI: `a` (HOST local part of the Hermitian A) is
+    overwritten in its `uplo` triangle with inv(L) A inv(L)^H / inv(U)^H A inv(U); `b` holds the Cholesky factor of B."""
+    n = a.shape[0] if n is None else n
+    da = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, _ld_of(a)))
+    db = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, _ld_of(b)))
+    return getattr(lib(), f"dlaf_b200_generalized_to_standard_{type_char(a.dtype)}")(ctx, uplo.encode(), a.ctypes.data, da,
+                                                                                     b.ctypes.data, db)
+
+
+def generalized_to_standard_device(ctx: int, uplo: str, a_dev: int, b_dev: int, dtype, n: int, nb: int, ld: int, stream: int = 0,
+                                   isrc: int = 0, jsrc: int = 0) -> int:
+    d = DLAF_descriptor(n, n, nb, nb, isrc, jsrc, 0, 0, max(1, ld))
+    return getattr(lib(), f"dlaf_b200_generalized_to_standard_device_{type_char(dtype)}")(ctx, uplo.encode(), a_dev, d, b_dev, d,
+                                                                                            stream)
 
 
 def last_inverse_guard_steps(ctx: int) -> int:

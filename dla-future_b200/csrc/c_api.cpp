@@ -22,6 +22,7 @@
 #include "common.h"
 #include "distribution.h"
 #include "engine.h"
+#include "hegst_engine.h"
 #include "inverse_engine.h"
 #include "trsm_engine.h"
 #include "util_matrix.h"
@@ -612,6 +613,83 @@ void pxpotri(char uplo, int n, T* a, int ia, int ja, const int desca[9], int* in
     *info = r;
 }
 
+// dlaf::eigensolver::internal::generalized_to_standard (include/dlaf/eigensolver/gen_to_std.h:50-127) on DEVICE local parts
+// (user layout): A in place, the Cholesky factor of B read only; collective over the grid of ctx, synchronous on `s`.
+template <class T>
+int hegst_on_device(int ctx, char uplo, T* a_dev, const DLAF_descriptor& da, const T* b_dev, const DLAF_descriptor& db,
+                    cudaStream_t s) {
+  using D = devtype_t<T>;
+  ensure_device();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return 0;
+  const CommGrid& g = *c.grid;
+  DLAF_B200_ASSERT(uplo == 'L' || uplo == 'l' || uplo == 'U' || uplo == 'u', "uplo must be L or U");
+  // preconditions of the reference (gen_to_std.h:51-60, :103-112)
+  DLAF_B200_ASSERT(da.m == da.n && da.mb == da.nb && db.m == db.n && db.mb == db.nb, "square matrices with square blocks");
+  DLAF_B200_ASSERT(da.m == db.m && da.mb == db.mb, "A and B must have the same size and block size");
+  DLAF_B200_ASSERT(da.i == 0 && da.j == 0 && db.i == 0 && db.j == 0, "sub-matrix offsets must be 0");
+  DLAF_B200_ASSERT(da.isrc == db.isrc && da.jsrc == db.jsrc && da.isrc >= 0 && da.isrc < g.P && da.jsrc >= 0 && da.jsrc < g.Q,
+                   "source rank");
+  HegstProblem p;
+  p.uplo = uplo;
+  p.n = da.n;
+  p.nb = da.nb;
+  p.P = g.P;
+  p.Q = g.Q;
+  p.prow = (g.row - da.isrc + g.P) % g.P;
+  p.pcol = (g.col - da.jsrc + g.Q) % g.Q;
+  p.src_row = da.isrc;
+  p.src_col = da.jsrc;
+  const long lr = local_size_1d(da.n, da.nb, g.P, p.prow);
+  DLAF_B200_ASSERT(da.ld >= std::max<long>(1, lr) && db.ld >= std::max<long>(1, lr), "leading dimension smaller than local rows");
+  cudaEvent_t e0, e1;
+  DLAF_CUDA_CHECK(cudaEventCreate(&e0));
+  DLAF_CUDA_CHECK(cudaEventCreate(&e1));
+  DLAF_CUDA_CHECK(cudaEventRecord(e0, s));
+  c.last_solver_launches = generalized_to_standard_device<D>(p, reinterpret_cast<D*>(a_dev), da.ld, reinterpret_cast<const D*>(b_dev),
+                                                             db.ld, g.row_comm, g.col_comm, s, &c.last_inverse_guard_steps);
+  DLAF_CUDA_CHECK(cudaEventRecord(e1, s));
+  DLAF_CUDA_CHECK(cudaEventSynchronize(e1));
+  DLAF_CUDA_CHECK(cudaEventElapsedTime(&c.last_solver_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+
+// ... on HOST local parts (MatrixMirror bracket of the reference's callers, eigensolver/gen_eigensolver/impl.h:37-38)
+template <class T>
+int hegst_host(int ctx, char uplo, T* a, const DLAF_descriptor& da, const T* b, const DLAF_descriptor& db) {
+  using D = devtype_t<T>;
+  ensure_device();
+  GridCtx& c = grid_from_context(ctx);
+  if (!c.grid->in_grid)
+    return 0;
+  const CommGrid& g = *c.grid;
+  DLAF_B200_ASSERT(da.isrc >= 0 && da.isrc < g.P && da.jsrc >= 0 && da.jsrc < g.Q, "source rank");
+  const int vrow = (g.row - da.isrc + g.P) % g.P, vcol = (g.col - da.jsrc + g.Q) % g.Q;
+  const long lr = local_size_1d(da.n, da.nb, g.P, vrow), lc = local_size_1d(da.n, da.nb, g.Q, vcol);
+  cudaStream_t s = ctx_stream(c);
+  D *dA = nullptr, *dB = nullptr;
+  const long ld = std::max<long>(lr, 1);
+  if (lr > 0 && lc > 0) {
+    DLAF_B200_ASSERT(da.ld >= lr && db.ld >= lr, "leading dimension smaller than local rows");
+    DLAF_CUDA_CHECK(cudaMalloc(&dA, sizeof(D) * ld * lc));
+    DLAF_CUDA_CHECK(cudaMalloc(&dB, sizeof(D) * ld * lc));
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dA, sizeof(D) * ld, a, sizeof(D) * da.ld, sizeof(D) * lr, lc, cudaMemcpyHostToDevice, s));
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dB, sizeof(D) * ld, b, sizeof(D) * db.ld, sizeof(D) * lr, lc, cudaMemcpyHostToDevice, s));
+  }
+  DLAF_descriptor dda = da, ddb = db;
+  dda.ld = ddb.ld = static_cast<int>(ld);
+  hegst_on_device<T>(ctx, uplo, reinterpret_cast<T*>(dA), dda, reinterpret_cast<const T*>(dB), ddb, s);
+  if (lr > 0 && lc > 0)
+    DLAF_CUDA_CHECK(cudaMemcpy2DAsync(a, sizeof(D) * da.ld, dA, sizeof(D) * ld, sizeof(D) * lr, lc, cudaMemcpyDeviceToHost, s));
+  DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
+  cudaFree(dA);
+  cudaFree(dB);
+  return 0;
+}
+
 template <class T>
 void random_hpd(int ctx, T* a, const DLAF_descriptor& desc) {
   ensure_initialized();
@@ -794,6 +872,15 @@ struct DLAF_descriptor make_dlaf_descriptor(const int m, const int n, const int 
   }                                                                                                           \
   int dlaf_b200_assemble_cholesky_inverse_##sfx(int ctx, char uplo, T* a, struct DLAF_descriptor d) noexcept { \
     return inverse_host<T>(ctx, kAssembleFromInverseFactor, uplo, 'N', a, d);                                 \
+  }                                                                                                           \
+  int dlaf_b200_generalized_to_standard_##sfx(int ctx, char uplo, T* a, struct DLAF_descriptor da, const T* b, \
+                                              struct DLAF_descriptor db) noexcept {                           \
+    return hegst_host<T>(ctx, uplo, a, da, b, db);                                                            \
+  }                                                                                                           \
+  int dlaf_b200_generalized_to_standard_device_##sfx(int ctx, char uplo, T* a_dev, struct DLAF_descriptor da, \
+                                                     const T* b_dev, struct DLAF_descriptor db,               \
+                                                     void* stream) noexcept {                                 \
+    return hegst_on_device<T>(ctx, uplo, a_dev, da, b_dev, db, static_cast<cudaStream_t>(stream));            \
   }                                                                                                           \
   int dlaf_b200_inverse_device_##sfx(int ctx, int phases, char uplo, char diag, T* a_dev,                     \
                                      struct DLAF_descriptor d, void* stream) noexcept {                       \

@@ -9,8 +9,7 @@
 #include "comm.h"
 #include "common.h"
 #include "distribution.h"
-#include "gemm_ozaki.h"
-#include "gemm_tf32.h"
+#include "bulk_update.cuh"
 #include "tri_kernels.cuh"
 
 namespace dlaf_b200 {
@@ -18,179 +17,6 @@ namespace dlaf_b200 {
 namespace {
 
 using namespace trik;
-
-// Caller's local part <-> padded lower-triangular engine slab (tiles nbp x nbp, ld = lds), 32 x 32 elements per CTA,
-// blockIdx.z = local tile (la + lb * ltr). Engine tile (ga, gb) = (la * Pe + erow, lb * Qe + ecol), element (r, c):
-//   not transposed: user local element (la * nb + r, lb * nb + c)
-//   transposed    : conj of user local element (lb * nb + c, la * nb + r)        (uplo == 'U': the engine works on A^H)
-// LOAD : tiles above the diagonal are skipped (the slab is zero there); diagonal tiles get zeros in their upper half,
-//        an identity in the padding and ones on the diagonal for Diag::Unit; everything else outside the matrix is zero.
-// STORE: only elements of the referenced triangle inside the matrix are written (not the diagonal for Diag::Unit).
-template <class T, bool LOAD>
-__global__ void inv_convert_kernel(T* __restrict__ a, long lda, T* __restrict__ slab, long lds, long n, int nb, int nbp,
-                                   int Pe, int Qe, int erow, int ecol, int ltr, bool transposed, bool unit) {
-  __shared__ T t[32][33];
-  const int la = blockIdx.z % ltr, lb = blockIdx.z / ltr;
-  const long ga = static_cast<long>(la) * Pe + erow, gb = static_cast<long>(lb) * Qe + ecol;
-  if (ga < gb)
-    return;
-  const int rows = static_cast<int>(max(0L, min(static_cast<long>(nb), n - ga * nb)));
-  const int cols = static_cast<int>(max(0L, min(static_cast<long>(nb), n - gb * nb)));
-  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  if (ga == gb && r0 + 31 < c0)
-    return;  // block strictly above the diagonal of a diagonal tile: zero in the slab, never stored
-  T* stile = slab + static_cast<long>(la) * nbp + static_cast<long>(lb) * nbp * lds;
-  const long ur0 = transposed ? static_cast<long>(lb) * nb : static_cast<long>(la) * nb;  // user local offset of the tile
-  const long uc0 = transposed ? static_cast<long>(la) * nb : static_cast<long>(lb) * nb;
-  const int tx = threadIdx.x;
-  if (LOAD) {
-    // phase 1: user -> t, coalesced along the user's rows
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-      const int r = transposed ? r0 + k : r0 + tx, c = transposed ? c0 + tx : c0 + k;  // engine element read here
-      T v = make_real<T>(0);
-      if (r < rows && c < cols)
-        v = transposed ? conj_val(a[(ur0 + c) + (uc0 + r) * lda]) : a[(ur0 + r) + (uc0 + c) * lda];
-      t[k][tx] = v;
-    }
-    __syncthreads();
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-      const int r = r0 + tx, c = c0 + k;
-      T v = transposed ? t[tx][k] : t[k][tx];
-      if (ga == gb) {
-        if (r < c)
-          v = make_real<T>(0);
-        else if (r == c && (unit || r >= rows))
-          v = make_real<T>(1);
-      }
-      stile[r + static_cast<long>(c) * lds] = v;
-    }
-  }
-  else {
-    for (int k = threadIdx.y; k < 32; k += blockDim.y)
-      t[k][tx] = stile[(r0 + tx) + static_cast<long>(c0 + k) * lds];  // t[c - c0][r - r0]
-    __syncthreads();
-    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
-      const int r = transposed ? r0 + k : r0 + tx, c = transposed ? c0 + tx : c0 + k;
-      const bool ref = (ga > gb) || (r > c) || (r == c && !unit);
-      if (r < rows && c < cols && ref) {
-        if (transposed)
-          a[(ur0 + c) + (uc0 + r) * lda] = conj_val(t[tx][k]);
-        else
-          a[(ur0 + r) + (uc0 + c) * lda] = t[k][tx];
-      }
-    }
-  }
-}
-
-// ntiles contiguous nbp x nbp tiles <- identity
-template <class T>
-__global__ void inv_identity_kernel(T* __restrict__ w, int nbp, long tile_stride) {
-  T* d = w + static_cast<long>(blockIdx.y) * tile_stride + static_cast<long>(blockIdx.x) * nbp;
-  for (int r = threadIdx.x; r < nbp; r += blockDim.x)
-    d[r] = make_real<T>(r == static_cast<int>(blockIdx.x) ? 1 : 0);
-}
-
-// One operand of a bulk update: `rows` rows x nbp columns, either plain column-major (tile_stride == 0, leading
-// dimension ld) or tile-contiguous (nbp x nbp tiles with leading dimension ld = nbp, tile_stride elements apart).
-template <class T>
-struct Operand {
-  const T* x;
-  long ld;
-  long rows;
-  long tile_stride;
-};
-
-// The one-launch-per-step update C = C + alpha A B^H on the engine of the element type: fp64 -> int8 digit planes on
-// tcgen05 + guarded native fallback, fp32 -> 3xTF32 on tcgen05, complex -> native kernels.
-template <class T>
-struct BulkUpdate {
-  bool oz = false, tf = false;
-  OzakiSplit oa, ob;
-  Tf32Split ta, tb;
-  int* flags = nullptr;
-  int nflags = 0, used = 0;
-
-  void init(long rows_a, long rows_b, int nbp, int nsteps, cudaStream_t s) {
-    if constexpr (std::is_same_v<T, double>) {
-      const char* e = std::getenv("DLAF_B200_D_BULK");
-      oz = (e == nullptr || std::string(e) == "ozaki") && nbp <= 512 && rows_a > 0 && rows_b > 0;
-      if (oz) {
-        oa.allocate(rows_a, nbp);
-        ob.allocate(rows_b, nbp);
-        nflags = nsteps;
-        DLAF_CUDA_CHECK(cudaMalloc(&flags, sizeof(int) * nflags));
-        DLAF_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * nflags, s));
-      }
-    }
-    if constexpr (std::is_same_v<T, float>) {
-      tf = std::getenv("DLAF_B200_S_SIMT") == nullptr && rows_a > 0 && rows_b > 0;
-      if (tf) {
-        ta.allocate(rows_a, nbp);
-        tb.allocate(rows_b, nbp);
-      }
-    }
-    (void) rows_a, (void) rows_b, (void) nbp, (void) nsteps, (void) s;
-  }
-
-  // g: C, ldc, M, N, K, alpha, mask geometry filled in; A / B described by the operands. same: B is the same panel as A.
-  long run(GemmArgsT<T> g, const Operand<T>& a, const Operand<T>& b, bool same, cudaStream_t s) {
-    if (g.M <= 0 || g.N <= 0)
-      return 0;
-    g.A = a.x;
-    g.lda = a.ld;
-    g.a_ts = a.tile_stride;
-    g.B = b.x;
-    g.ldb = b.ld;
-    g.b_ts = b.tile_stride;
-    g.beta = 1.0;
-    if constexpr (std::is_same_v<T, double>) {
-      if (oz) {
-        DLAF_B200_ASSERT(used < nflags, "guard flags exhausted");
-        int* flag = flags + used++;
-        oa.split(a.x, a.ld, a.rows, s, a.tile_stride ? g.nbp : 0, a.tile_stride, flag);
-        if (!same)
-          ob.split(b.x, b.ld, b.rows, s, b.tile_stride ? g.nbp : 0, b.tile_stride, flag);
-        launch_gemm_ozaki_i8(g, oa, 0, same ? oa : ob, 0, s, 0, flag);
-        launch_gemm_nt_f64_if(g, flag, s);
-        return same ? 3 : 4;
-      }
-    }
-    if constexpr (std::is_same_v<T, float>) {
-      if (tf) {
-        ta.split(a.x, a.ld, a.rows, s, a.tile_stride ? g.nbp : 0, a.tile_stride);
-        if (!same)
-          tb.split(b.x, b.ld, b.rows, s, b.tile_stride ? g.nbp : 0, b.tile_stride);
-        launch_gemm_tf32x3(g, ta, 0, same ? ta : tb, 0, s);
-        return same ? 2 : 3;
-      }
-    }
-    launch_gemm_nt<T>(g, s);
-    return 1;
-  }
-
-  // number of steps whose guard fired (synchronises the stream); releases everything
-  int finish(cudaStream_t s) {
-    int fired = 0;
-    if (oz) {
-      DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-      if (used > 0) {
-        std::vector<int> h(used);
-        DLAF_CUDA_CHECK(cudaMemcpy(h.data(), flags, sizeof(int) * used, cudaMemcpyDeviceToHost));
-        for (int v : h)
-          fired += (v != 0);
-      }
-      oa.release();
-      ob.release();
-      cudaFree(flags);
-    }
-    if (tf) {
-      DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-      ta.release();
-      tb.release();
-    }
-    return fired;
-  }
-};
 
 }  // namespace
 
@@ -233,7 +59,7 @@ long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, nc
     DLAF_CUDA_CHECK(cudaMemsetAsync(slab, 0, sizeof(T) * lds * ltc * nbp, s));
     dim3 grid(nbp / 32, nbp / 32, ltr * ltc), block(32, 8);
     inv_convert_kernel<T, true><<<grid, block, 0, s>>>(a_user, lda, slab, lds, p.n, p.nb, nbp, Pe, Qe, erow, ecol, ltr, transposed,
-                                                       unit);
+                                                       unit, true);
     DLAF_CUDA_CHECK(cudaGetLastError());
     ++launches;
   }
@@ -436,7 +262,7 @@ long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, nc
   if (have) {
     dim3 grid(nbp / 32, nbp / 32, ltr * ltc), block(32, 8);
     inv_convert_kernel<T, false><<<grid, block, 0, s>>>(a_user, lda, slab, lds, p.n, p.nb, nbp, Pe, Qe, erow, ecol, ltr,
-                                                        transposed, unit);
+                                                        transposed, unit, true);
     DLAF_CUDA_CHECK(cudaGetLastError());
     ++launches;
   }

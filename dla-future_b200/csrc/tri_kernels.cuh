@@ -203,6 +203,78 @@ inline long solve_rows_against_tile(T* y, long ldy, long m, const T* gkk, long l
   return launches;
 }
 
+// Caller's local part <-> padded lower-triangular engine slab (tiles nbp x nbp, ld = lds), 32 x 32 elements per CTA,
+// blockIdx.z = local tile (la + lb * ltr). Engine tile (ga, gb) = (la * Pe + erow, lb * Qe + ecol), element (r, c):
+//   not transposed: user local element (la * nb + r, lb * nb + c)
+//   transposed    : conj of user local element (lb * nb + c, la * nb + r)        (uplo == 'U': the engine works on A^H)
+// LOAD : tiles above the diagonal are skipped (the slab is zero there); diagonal tiles get zeros in their upper half,
+//        an identity in the padding (pad_identity) and ones on the diagonal for Diag::Unit; everything else outside the matrix is zero.
+// STORE: only elements of the referenced triangle inside the matrix are written (not the diagonal for Diag::Unit).
+template <class T, bool LOAD>
+__global__ void inv_convert_kernel(T* __restrict__ a, long lda, T* __restrict__ slab, long lds, long n, int nb, int nbp,
+                                   int Pe, int Qe, int erow, int ecol, int ltr, bool transposed, bool unit,
+                                   bool pad_identity) {
+  __shared__ T t[32][33];
+  const int la = blockIdx.z % ltr, lb = blockIdx.z / ltr;
+  const long ga = static_cast<long>(la) * Pe + erow, gb = static_cast<long>(lb) * Qe + ecol;
+  if (ga < gb)
+    return;
+  const int rows = static_cast<int>(max(0L, min(static_cast<long>(nb), n - ga * nb)));
+  const int cols = static_cast<int>(max(0L, min(static_cast<long>(nb), n - gb * nb)));
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (ga == gb && r0 + 31 < c0)
+    return;  // block strictly above the diagonal of a diagonal tile: zero in the slab, never stored
+  T* stile = slab + static_cast<long>(la) * nbp + static_cast<long>(lb) * nbp * lds;
+  const long ur0 = transposed ? static_cast<long>(lb) * nb : static_cast<long>(la) * nb;  // user local offset of the tile
+  const long uc0 = transposed ? static_cast<long>(la) * nb : static_cast<long>(lb) * nb;
+  const int tx = threadIdx.x;
+  if (LOAD) {
+    // phase 1: user -> t, coalesced along the user's rows
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+      const int r = transposed ? r0 + k : r0 + tx, c = transposed ? c0 + tx : c0 + k;  // engine element read here
+      T v = make_real<T>(0);
+      if (r < rows && c < cols)
+        v = transposed ? conj_val(a[(ur0 + c) + (uc0 + r) * lda]) : a[(ur0 + r) + (uc0 + c) * lda];
+      t[k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+      const int r = r0 + tx, c = c0 + k;
+      T v = transposed ? t[tx][k] : t[k][tx];
+      if (ga == gb) {
+        if (r < c)
+          v = make_real<T>(0);
+        else if (r == c && (unit || (pad_identity && r >= rows)))
+          v = make_real<T>(1);
+      }
+      stile[r + static_cast<long>(c) * lds] = v;
+    }
+  }
+  else {
+    for (int k = threadIdx.y; k < 32; k += blockDim.y)
+      t[k][tx] = stile[(r0 + tx) + static_cast<long>(c0 + k) * lds];  // t[c - c0][r - r0]
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+      const int r = transposed ? r0 + k : r0 + tx, c = transposed ? c0 + tx : c0 + k;
+      const bool ref = (ga > gb) || (r > c) || (r == c && !unit);
+      if (r < rows && c < cols && ref) {
+        if (transposed)
+          a[(ur0 + c) + (uc0 + r) * lda] = conj_val(t[tx][k]);
+        else
+          a[(ur0 + r) + (uc0 + c) * lda] = t[k][tx];
+      }
+    }
+  }
+}
+
+// ntiles contiguous nbp x nbp tiles <- identity
+template <class T>
+__global__ void inv_identity_kernel(T* __restrict__ w, int nbp, long tile_stride) {
+  T* d = w + static_cast<long>(blockIdx.y) * tile_stride + static_cast<long>(blockIdx.x) * nbp;
+  for (int r = threadIdx.x; r < nbp; r += blockDim.x)
+    d[r] = make_real<T>(r == static_cast<int>(blockIdx.x) ? 1 : 0);
+}
+
 inline int cnt(long g_end, int v, int grid) {  // tiles of virtual rank v with global index < g_end
   return static_cast<int>(next_local_tile_from_global_tile(g_end, grid, v, 0));
 }

@@ -49,7 +49,20 @@ DLAF_EXTERN_C int dlaf_b200_inverse_device_s(int ctx, int phases, char uplo, cha
 DLAF_EXTERN_C int dlaf_b200_inverse_device_d(int ctx, int phases, char uplo, char diag, double* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
 DLAF_EXTERN_C int dlaf_b200_inverse_device_c(int ctx, int phases, char uplo, char diag, dlaf_complex_c* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
 DLAF_EXTERN_C int dlaf_b200_inverse_device_z(int ctx, int phases, char uplo, char diag, dlaf_complex_z* a_dev, struct DLAF_descriptor desc, void* cuda_stream) DLAF_NOEXCEPT;
-/* fp64: number of steps of the last inverse on ctx whose update ran on the native fp64 kernel because the int8 digit
+/* dlaf::eigensolver::internal::generalized_to_standard (include/dlaf/eigensolver/gen_to_std.h:50-127; the reference
+ * reaches it only through its generalized eigensolver): the `uplo` triangle of the Hermitian matrix A (HOST local part a)
+ * is overwritten with that of inv(L) A inv(L)^H ('L') / inv(U)^H A inv(U) ('U'), where b holds the Cholesky factor of B
+ * in its `uplo` triangle (the output of dlaf_cholesky_factorization_*; read only). A and B: same size, block size, source
+ * rank. Collective over the grid of ctx, synchronous. Returns 0. The _device flavour takes DEVICE local parts. */
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_s(int ctx, char uplo, float* a, struct DLAF_descriptor desca, const float* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_d(int ctx, char uplo, double* a, struct DLAF_descriptor desca, const double* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_c(int ctx, char uplo, dlaf_complex_c* a, struct DLAF_descriptor desca, const dlaf_complex_c* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_z(int ctx, char uplo, dlaf_complex_z* a, struct DLAF_descriptor desca, const dlaf_complex_z* b, struct DLAF_descriptor descb) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_device_s(int ctx, char uplo, float* a_dev, struct DLAF_descriptor desca, const float* b_dev, struct DLAF_descriptor descb, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_device_d(int ctx, char uplo, double* a_dev, struct DLAF_descriptor desca, const double* b_dev, struct DLAF_descriptor descb, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_device_c(int ctx, char uplo, dlaf_complex_c* a_dev, struct DLAF_descriptor desca, const dlaf_complex_c* b_dev, struct DLAF_descriptor descb, void* cuda_stream) DLAF_NOEXCEPT;
+DLAF_EXTERN_C int dlaf_b200_generalized_to_standard_device_z(int ctx, char uplo, dlaf_complex_z* a_dev, struct DLAF_descriptor desca, const dlaf_complex_z* b_dev, struct DLAF_descriptor descb, void* cuda_stream) DLAF_NOEXCEPT;
+/* fp64: number of steps of the last inverse / generalized_to_standard on ctx whose update ran on the native fp64 kernel because the int8 digit
  * guard fired (see dlaf_b200_guard_fallback_steps). */
 DLAF_EXTERN_C int dlaf_b200_last_inverse_guard_steps(int ctx) DLAF_NOEXCEPT;
 /* Number of this library's kernel launches issued by the last triangular solve / inverse on ctx. */

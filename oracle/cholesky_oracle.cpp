@@ -25,6 +25,9 @@
 //                              closed forms of test/include/dlaf_test/matrix/util_generic_blas.h:259-371
 //   * triangular_inverse_local include/dlaf/inverse/triangular/impl.h:183-229 (call_L) and :367-413 (call_U), tile ops
 //                              :47-110 / :112-170; pinned to test/include/dlaf_test/matrix/util_generic_lapack.h:261-327
+//   * generalized_to_standard_local   include/dlaf/eigensolver/gen_to_std/impl.h:238-281 (call_L) and :507-568 (call_U), tile
+//                              ops :43-146 / :148-233; pinned to util_generic_lapack.h:94-149 (itype 1), test table and
+//                              tolerance of test/unit/eigensolver/test_gen_to_std.cpp:52-56, :78
 //   * assemble_cholesky_inverse_local  include/dlaf/inverse/cholesky/impl.h:180-224 (call_L) and :361-405 (call_U), tile
 //                              ops :46-108 / :110-172; pinned to util_generic_lapack.h:165-196 and, chained after the
 //                              triangular inverse (include/dlaf/inverse/cholesky.h:38-52), to :212-247
@@ -63,6 +66,21 @@ DECL_REAL(s, float)
 DECL_REAL(d, double)
 DECL_REAL(c, std::complex<float>)
 DECL_REAL(z, std::complex<double>)
+void scipy_ssygst_(const int*, const char*, const int*, float*, const int*, const float*, const int*, int*);
+void scipy_dsygst_(const int*, const char*, const int*, double*, const int*, const double*, const int*, int*);
+void scipy_chegst_(const int*, const char*, const int*, std::complex<float>*, const int*, const std::complex<float>*,
+                   const int*, int*);
+void scipy_zhegst_(const int*, const char*, const int*, std::complex<double>*, const int*, const std::complex<double>*,
+                   const int*, int*);
+#define DECL_HE(p, hemm, her2k, T, R)                                                                                   \
+  void scipy_##p##hemm##_(const char*, const char*, const int*, const int*, const T*, const T*, const int*, const T*,   \
+                          const int*, const T*, T*, const int*);                                                        \
+  void scipy_##p##her2k##_(const char*, const char*, const int*, const int*, const T*, const T*, const int*, const T*, \
+                           const int*, const R*, T*, const int*);
+DECL_HE(s, symm, syr2k, float, float)
+DECL_HE(d, symm, syr2k, double, double)
+DECL_HE(c, hemm, her2k, std::complex<float>, float)
+DECL_HE(z, hemm, her2k, std::complex<double>, double)
 void scipy_ssyrk_(const char*, const char*, const int*, const int*, const float*, const float*,
                   const int*, const float*, float*, const int*);
 void scipy_dsyrk_(const char*, const char*, const int*, const int*, const double*, const double*,
@@ -562,6 +580,103 @@ void assemble_cholesky_inverse_local(char uplo, long n, long nb, T* a, long lda)
   }
 }
 
+
+inline int hegst(int itype, char uplo, int n, float* a, int lda, const float* b, int ldb) {
+  int info = 0;
+  scipy_ssygst_(&itype, &uplo, &n, a, &lda, b, &ldb, &info);
+  return info;
+}
+inline int hegst(int itype, char uplo, int n, double* a, int lda, const double* b, int ldb) {
+  int info = 0;
+  scipy_dsygst_(&itype, &uplo, &n, a, &lda, b, &ldb, &info);
+  return info;
+}
+inline int hegst(int itype, char uplo, int n, std::complex<float>* a, int lda, const std::complex<float>* b, int ldb) {
+  int info = 0;
+  scipy_chegst_(&itype, &uplo, &n, a, &lda, b, &ldb, &info);
+  return info;
+}
+inline int hegst(int itype, char uplo, int n, std::complex<double>* a, int lda, const std::complex<double>* b, int ldb) {
+  int info = 0;
+  scipy_zhegst_(&itype, &uplo, &n, a, &lda, b, &ldb, &info);
+  return info;
+}
+#define WRAP_HE(p, hemm_, her2k_, T, R)                                                                              \
+  inline void hemm(char side, char uplo, int m, int n, T alpha, const T* a, int lda, const T* b, int ldb, T beta,   \
+                   T* c, int ldc) {                                                                                  \
+    scipy_##p##hemm_##_(&side, &uplo, &m, &n, &alpha, a, &lda, b, &ldb, &beta, c, &ldc);                             \
+  }                                                                                                                  \
+  inline void her2k(char uplo, char op, int n, int k, T alpha, const T* a, int lda, const T* b, int ldb, R beta,    \
+                    T* c, int ldc) {                                                                                 \
+    scipy_##p##her2k_##_(&uplo, &op, &n, &k, &alpha, a, &lda, b, &ldb, &beta, c, &ldc);                              \
+  }
+WRAP_HE(s, symm, syr2k, float, float)
+WRAP_HE(d, symm, syr2k, double, double)
+WRAP_HE(c, hemm, her2k, std::complex<float>, float)
+WRAP_HE(z, hemm, her2k, std::complex<double>, double)
+
+// ---- generalized to standard ------------------------------------------------------------------
+// Restatement of GenToStd<B,D,T>::call_L / call_U (LOCAL), include/dlaf/eigensolver/gen_to_std/impl.h:238-281, :507-568
+// (the blocked xHEGST, itype 1): per step the tile hegst, the panel TRSM + first HEMM, the HER2K / two GEMMs of the
+// trailing matrix, the second HEMM and the panel solve against the trailing factor.
+template <class T>
+void generalized_to_standard_local(char uplo, long n, long nb, T* a, long lda, const T* l, long ldl) {
+  if (n == 0)
+    return;
+  using R = BaseT<T>;
+  const char CT = std::is_same_v<T, R> ? 'T' : 'C';
+  const long nt = (n + nb - 1) / nb;
+  auto sz = [&](long i) { return static_cast<int>(std::min(nb, n - i * nb)); };
+  auto A = [&](long i, long j) { return a + i * nb + j * nb * lda; };
+  auto L = [&](long i, long j) { return l + i * nb + j * nb * ldl; };
+  const int la = static_cast<int>(lda), ll = static_cast<int>(ldl);
+  for (long k = 0; k < nt; ++k) {
+    hegst(1, uplo, sz(k), A(k, k), la, L(k, k), ll);  // impl.h:43-51, :245
+    if (k == nt - 1)
+      continue;
+    if (uplo == 'L') {
+      for (long i = k + 1; i < nt; ++i) {
+        trsm('R', 'L', CT, 'N', sz(i), sz(k), T(1), L(k, k), ll, A(i, k), la);                              // :53-64
+        hemm('R', 'L', sz(i), sz(k), T(-0.5), A(k, k), la, L(i, k), ll, T(1), A(i, k), la);                 // :66-78
+      }
+      for (long j = k + 1; j < nt; ++j) {
+        her2k('L', 'N', sz(j), sz(k), T(-1), A(j, k), la, L(j, k), ll, R(1), A(j, j), la);                  // :80-92
+        for (long i = j + 1; i < nt; ++i) {
+          gemm('N', CT, sz(i), sz(j), sz(k), T(-1), A(i, k), la, L(j, k), ll, T(1), A(i, j), la);           // :94-106
+          gemm('N', CT, sz(i), sz(j), sz(k), T(-1), L(i, k), ll, A(j, k), la, T(1), A(i, j), la);
+        }
+      }
+      for (long i = k + 1; i < nt; ++i)
+        hemm('R', 'L', sz(i), sz(k), T(-0.5), A(k, k), la, L(i, k), ll, T(1), A(i, k), la);
+      for (long j = k + 1; j < nt; ++j) {
+        trsm('L', 'L', 'N', 'N', sz(j), sz(k), T(1), L(j, j), ll, A(j, k), la);                             // :108-119
+        for (long i = j + 1; i < nt; ++i)
+          gemm('N', 'N', sz(i), sz(k), sz(j), T(-1), L(i, j), ll, A(j, k), la, T(1), A(i, k), la);          // :121-133
+      }
+    }
+    else {
+      for (long i = k + 1; i < nt; ++i) {
+        trsm('L', 'U', CT, 'N', sz(k), sz(i), T(1), L(k, k), ll, A(k, i), la);                              // :158-169
+        hemm('L', 'U', sz(k), sz(i), T(-0.5), A(k, k), la, L(k, i), ll, T(1), A(k, i), la);                 // :171-183
+      }
+      for (long i = k + 1; i < nt; ++i) {
+        her2k('U', CT, sz(i), sz(k), T(-1), A(k, i), la, L(k, i), ll, R(1), A(i, i), la);                   // :185-197
+        for (long j = i + 1; j < nt; ++j) {
+          gemm(CT, 'N', sz(i), sz(j), sz(k), T(-1), A(k, i), la, L(k, j), ll, T(1), A(i, j), la);           // :199-211
+          gemm(CT, 'N', sz(i), sz(j), sz(k), T(-1), L(k, i), ll, A(k, j), la, T(1), A(i, j), la);
+        }
+      }
+      for (long i = k + 1; i < nt; ++i)
+        hemm('L', 'U', sz(k), sz(i), T(-0.5), A(k, k), la, L(k, i), ll, T(1), A(k, i), la);
+      for (long i = k + 1; i < nt; ++i) {
+        trsm('R', 'U', 'N', 'N', sz(k), sz(i), T(1), L(i, i), ll, A(k, i), la);                             // :213-224
+        for (long j = i + 1; j < nt; ++j)
+          gemm('N', 'N', sz(k), sz(j), sz(i), T(-1), A(k, i), la, L(i, j), ll, T(1), A(k, j), la);          // :226-238
+      }
+    }
+  }
+}
+
 }  // namespace
 
 #define EXPORT_TYPE(sfx, T)                                                                      \
@@ -582,6 +697,10 @@ void assemble_cholesky_inverse_local(char uplo, long n, long nb, T* a, long lda)
                                                  long ldb) {                                     \
     triangular_solver_local<T>(side, uplo, op, diag, *static_cast<const T*>(alpha), m, n, mb, nb, \
                                static_cast<const T*>(a), lda, static_cast<T*>(b), ldb);          \
+  }                                                                                              \
+  extern "C" void oracle_generalized_to_standard_##sfx(char uplo, long n, long nb, void* a, long lda, \
+                                                       const void* l, long ldl) {                 \
+    generalized_to_standard_local<T>(uplo, n, nb, static_cast<T*>(a), lda, static_cast<const T*>(l), ldl); \
   }                                                                                              \
   extern "C" void oracle_triangular_inverse_##sfx(char uplo, char diag, long n, long nb, void* a, \
                                                   long lda) {                                    \

@@ -397,6 +397,51 @@ def inverse_tolerance(m: int, dtype) -> float:
     return 4 * (m + 1) * type_error(dtype)
 
 
+# ---------------------------------------------------------------------------------------------
+# Generalized -> standard eigenproblem (HEGST, itype 1): the reference's local tile loops
+# (oracle_generalized_to_standard_*) and its closed form (getGenToStdElementSetters,
+# test/include/dlaf_test/matrix/util_generic_lapack.h:94-149) with the parameters, sizes and tolerance of
+# test/unit/eigensolver/test_gen_to_std.cpp:52-56, :64-66, :78.
+# ---------------------------------------------------------------------------------------------
+GEN_TO_STD_TEST_SIZES = [(0, 2), (5, 8), (34, 34), (4, 3), (16, 10), (34, 13), (32, 5)]  # (m, mb)
+GEN_TO_STD_PARAMS = (-2.0, 1.5, 0.95)  # alpha, beta, gamma
+
+
+def generalized_to_standard(uplo: str, a: np.ndarray, l: np.ndarray, nb: int) -> None:
+    """In place on the Fortran-ordered a: `uplo` triangle of inv(L) A inv(L)^H ('L') / inv(U)^H A inv(U) ('U'); l holds the
+    Cholesky factor of B in its `uplo` triangle (read only)."""
+    _check_fortran(a)
+    _check_fortran(l)
+    n = a.shape[0]
+    assert a.shape == (n, n) and l.shape == (n, n) and a.dtype == l.dtype
+    if n == 0:
+        return
+    f = getattr(lib(), f"oracle_generalized_to_standard_{type_char(a.dtype)}")
+    cc, cl, vp = ctypes.c_char, ctypes.c_long, ctypes.c_void_p
+    f.argtypes = [cc, cl, cl, vp, cl, vp, cl]
+    f.restype = None
+    f(uplo.upper().encode(), n, nb, a.ctypes.data, max(1, a.strides[1] // a.itemsize), l.ctypes.data,
+      max(1, l.strides[1] // l.itemsize))
+
+
+def gen_to_std_setters(uplo: str, n: int, dtype, params=GEN_TO_STD_PARAMS):
+    """(T, A, B) of getGenToStdElementSetters(n, itype = 1, uplo, alpha, beta, gamma): B = inv(T) A inv(T)^H (Lower) /
+    inv(T)^H A inv(T) (Upper); unreferenced entries hold the sentinel."""
+    dtype = np.dtype(dtype)
+    alpha, beta, gamma = params
+    i, j = _ij(n)
+    unref = _unref(uplo, i, j)
+    t = _polar(beta / np.exp2(np.abs(i - j)), alpha * (i - j), dtype)
+    a = _polar((i + 1) * (j + 1) * (beta * beta * gamma) / np.exp2(i + j), alpha * (i - j), dtype)
+    b = _polar(gamma / np.exp2(i + j), alpha * (i - j), dtype)
+    return _finish(t, unref, dtype), _finish(a, unref, dtype), _finish(b, unref, dtype)
+
+
+def gen_to_std_tolerance(m: int, dtype) -> float:
+    """absolute 10 (m + 1) error, no relative criterion (test_gen_to_std.cpp:78)."""
+    return 10 * (m + 1) * type_error(dtype)
+
+
 # Sizes of the reference's algorithm test (test/unit/factorization/test_cholesky.cpp:54-58): (m, mb)
 CHOLESKY_TEST_SIZES = [(0, 2), (5, 8), (34, 34), (4, 3), (16, 10), (34, 13), (32, 5)]
 

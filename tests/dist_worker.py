@@ -266,6 +266,48 @@ def main():
                     ok, _, msg = O.check_near(np.where(lsent, lref / scale, lref), np.where(lsent, work / scale, work), tol, tol)
                     if not ok:
                         failures.append(("potri big", t, uplo, m, mb, msg))
+    if a.mode == "gpu":
+        # ---- distributed generalized -> standard (test/unit/eigensolver/test_gen_to_std.cpp:81-110): closed form on the grid with
+        # a non-zero source rank (the factor must come back unchanged), then a random pencil vs the oracle
+        for (m, mb) in [(16, 10), (34, 13), (32, 5), (4, 3)]:
+            for t in "sdcz":
+                dt = pkg.TYPES[t]
+                for uplo in "LU":
+                    T0, A0, B0 = O.gen_to_std_setters(uplo, m, dt)
+                    loc_a, work_a = local_of(A0, mb, dt)
+                    loc_t, work_t = local_of(T0, mb, dt)
+                    t_before = work_t.copy(order="F")
+                    pkg.generalized_to_standard(ctx, uplo, work_a, work_t, mb, n=m, isrc=src[0], jsrc=src[1])
+                    if rank < P * Q and loc_a.size:
+                        ok, _, msg = O.check_near(O.scatter_block_cyclic(B0, mb, (P, Q), src)[(myrow, mycol)], work_a, 0.0,
+                                                  O.gen_to_std_tolerance(m, dt))
+                        if not ok:
+                            failures.append(("hegst", t, uplo, m, mb, msg))
+                        if not np.array_equal(work_t, t_before):
+                            failures.append(("hegst factor modified", t, uplo, m, mb))
+        for (m, mb, t) in [(1536, 256, "d"), (1100, 200, "d"), (768, 128, "z"), (1024, 256, "s")]:
+            dt = pkg.TYPES[t]
+            for uplo in "LU":
+                A0 = O.set_random_hermitian_positive_definite(m, mb, dt)
+                B0 = O.set_random_hermitian_positive_definite(m, mb, dt)
+                B0 = np.asfortranarray(B0 + B0.conj().T)
+                fac = B0.copy(order="F")
+                assert O.cholesky_local(uplo, fac, mb, 4) == 0
+                tri = np.tril if uplo == "L" else np.triu
+                sent = np.full((m, m), -9.9)
+                sent = (np.triu(sent, 1) if uplo == "L" else np.tril(sent, -1)).astype(dt)
+                fac = np.asfortranarray(tri(fac) + sent)
+                a_in = np.asfortranarray(tri(A0) + sent)
+                ref = a_in.copy(order="F")
+                O.generalized_to_standard(uplo, ref, fac, mb)
+                loc_a, work_a = local_of(a_in, mb, dt)
+                loc_t, work_t = local_of(fac, mb, dt)
+                pkg.generalized_to_standard(ctx, uplo, work_a, work_t, mb, n=m, isrc=src[0], jsrc=src[1])
+                if rank < P * Q and loc_a.size:
+                    tol = O.gen_to_std_tolerance(m, dt) * max(1.0, float(np.abs(tri(ref)).max()))
+                    ok, _, msg = O.check_near(O.scatter_block_cyclic(ref, mb, (P, Q), src)[(myrow, mycol)], work_a, 0.0, tol)
+                    if not ok:
+                        failures.append(("hegst big", t, uplo, m, mb, msg))
     flag = torch.tensor([len(failures)], dtype=torch.int64, device="cuda" if a.mode == "gpu" else "cpu")
     dist.all_reduce(flag)
     if failures:

@@ -8,7 +8,7 @@ LIBDIR    := dla-future_b200/lib
 LIB       := $(LIBDIR)/libdlaf_b200.so
 
 CU_OBJS  := build/gemm_dmma.o build/gemm_simt.o build/gemm_zdmma.o build/gemm_tf32_tcgen05.o build/gemm_ozaki_i8.o build/potrf_tile.o build/potrf_tile_cluster.o build/layout.o build/engine.o build/sm_partition.o build/peak.o build/engine_check.o build/trsm_engine.o build/inverse_engine.o build/hegst_engine.o
-CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o
+CPP_OBJS := build/comm.o build/c_api.o build/util_matrix.o build/pool.o
 OBJS     := $(CU_OBJS) $(CPP_OBJS)
 HDRS     := $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) $(wildcard include/dlaf_c/*.h) $(wildcard include/dlaf_c/factorization/*.h) $(wildcard include/dlaf_c/inverse/*.h)
 
@@ -28,8 +28,8 @@ $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lnccl -lpthread
 
-tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_tile.o build/potrf_tile_cluster.o build/gemm_tf32_tcgen05.o $(HDRS)
-	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/potrf_tile.o build/potrf_tile_cluster.o build/gemm_tf32_tcgen05.o -lcublas -o $@
+tools/gpu_kernel_test: tools/gpu_kernel_test.cu build/gemm_dmma.o build/potrf_tile.o build/potrf_tile_cluster.o build/gemm_tf32_tcgen05.o build/pool.o $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/potrf_tile.o build/potrf_tile_cluster.o build/gemm_tf32_tcgen05.o build/pool.o -lcublas -o $@
 
 tools/gpu_diag_tile_test: tools/gpu_diag_tile_test.cu build/potrf_tile_cluster.o $(HDRS)
 	$(NVCC) $(NVCCFLAGS) $< build/potrf_tile_cluster.o -o $@
@@ -37,8 +37,8 @@ tools/gpu_diag_tile_test: tools/gpu_diag_tile_test.cu build/potrf_tile_cluster.o
 tools/gpu_chain_test: tools/gpu_chain_test.cu build/gemm_dmma.o $(HDRS)
 	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o -o $@
 
-tools/gpu_ozaki_test: tools/gpu_ozaki_test.cu build/gemm_dmma.o build/gemm_ozaki_i8.o $(HDRS)
-	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/gemm_ozaki_i8.o -o $@
+tools/gpu_ozaki_test: tools/gpu_ozaki_test.cu build/gemm_dmma.o build/gemm_ozaki_i8.o build/pool.o $(HDRS)
+	$(NVCC) $(NVCCFLAGS) $< build/gemm_dmma.o build/gemm_ozaki_i8.o build/pool.o -o $@
 
 # vendor-library GPU reference (measurement aid only; nothing in the product links cuSOLVER)
 tools/cusolver_potrf_ref: tools/cusolver_potrf_ref.cu

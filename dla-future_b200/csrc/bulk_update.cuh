@@ -14,6 +14,7 @@
 #include "gemm_args.h"
 #include "gemm_ozaki.h"
 #include "gemm_tf32.h"
+#include "pool.h"
 
 namespace dlaf_b200 {
 
@@ -37,6 +38,8 @@ struct BulkUpdate {
   int* flags = nullptr;
   int nflags = 0, used = 0;
   int* cur = nullptr;  // guard flag of the current step
+  OzakiSplit ox;       // one extra small B-side operand per step (a single tile: the diagonal tile of the reduction)
+  Tf32Split tx;
 
   // rows_a / rows_b: largest number of rows of an A-side / B-side operand; nslots operands per side and step
   void init(long rows_a, long rows_b, int nbp, int nsteps, cudaStream_t s, int nslots = 1) {
@@ -50,7 +53,7 @@ struct BulkUpdate {
           ob[i].allocate(rows_b, nbp);
         }
         nflags = nsteps;
-        DLAF_CUDA_CHECK(cudaMalloc(&flags, sizeof(int) * nflags));
+        flags = pool_alloc<int>(nflags);
         DLAF_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * nflags, s));
       }
     }
@@ -64,6 +67,57 @@ struct BulkUpdate {
       }
     }
     (void) rows_a, (void) rows_b, (void) nbp, (void) nsteps, (void) s;
+  }
+
+  void init_extra(long rows, int nbp) {
+    if (oz)
+      ox.allocate(rows, nbp);
+    if (tf)
+      tx.allocate(rows, nbp);
+  }
+  long split_extra(const Operand<T>& o, int nbp, cudaStream_t s) {
+    if constexpr (std::is_same_v<T, double>) {
+      if (oz) {
+        ox.split(o.x, o.ld, o.rows, s, o.tile_stride ? nbp : 0, o.tile_stride, cur);
+        return 1;
+      }
+    }
+    if constexpr (std::is_same_v<T, float>) {
+      if (tf) {
+        tx.split(o.x, o.ld, o.rows, s, o.tile_stride ? nbp : 0, o.tile_stride);
+        return 1;
+      }
+    }
+    (void) o, (void) nbp, (void) s;
+    return 0;
+  }
+  // C += alpha A B^H with A = slot ia of the A side and B = the extra operand (g.alpha = +-2^e for fp64)
+  long gemm_extra(GemmArgsT<T> g, const Operand<T>& a, int ia, const Operand<T>& b, cudaStream_t s) {
+    if (g.M <= 0 || g.N <= 0)
+      return 0;
+    g.A = a.x;
+    g.lda = a.ld;
+    g.a_ts = a.tile_stride;
+    g.B = b.x;
+    g.ldb = b.ld;
+    g.b_ts = b.tile_stride;
+    g.beta = 1.0;
+    if constexpr (std::is_same_v<T, double>) {
+      if (oz) {
+        launch_gemm_ozaki_i8(g, oa[ia], 0, ox, 0, s, 0, cur);
+        launch_gemm_nt_f64_if(g, cur, s);
+        return 2;
+      }
+    }
+    if constexpr (std::is_same_v<T, float>) {
+      if (tf) {
+        launch_gemm_tf32x3(g, ta[ia], 0, tx, 0, s);
+        return 1;
+      }
+    }
+    (void) ia;
+    launch_gemm_nt<T>(g, s);
+    return 1;
   }
 
   // ---- step-wise interface: begin_step, split the operands of the step once, then any number of products
@@ -147,7 +201,8 @@ struct BulkUpdate {
         oa[i].release();
         ob[i].release();
       }
-      cudaFree(flags);
+      ox.release();
+      pool_free(flags);
     }
     if (tf) {
       DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -155,6 +210,7 @@ struct BulkUpdate {
         ta[i].release();
         tb[i].release();
       }
+      tx.release();
     }
     return fired;
   }

@@ -24,6 +24,7 @@
 #include "engine.h"
 #include "hegst_engine.h"
 #include "inverse_engine.h"
+#include "pool.h"
 #include "trsm_engine.h"
 #include "util_matrix.h"
 
@@ -503,11 +504,11 @@ int triangular_solver_host(int ctx, char side, char uplo, char op, char diag, co
   D *dA = nullptr, *dB = nullptr;
   const long ldA = std::max<long>(lra, 1), ldB = std::max<long>(lrb, 1);
   if (lra > 0 && lca > 0) {
-    DLAF_CUDA_CHECK(cudaMalloc(&dA, sizeof(D) * ldA * lca));
+    dA = pool_alloc<D>(ldA * lca);
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dA, sizeof(D) * ldA, a, sizeof(D) * da.ld, sizeof(D) * lra, lca, cudaMemcpyHostToDevice, s));
   }
   if (lrb > 0 && lcb > 0) {
-    DLAF_CUDA_CHECK(cudaMalloc(&dB, sizeof(D) * ldB * lcb));
+    dB = pool_alloc<D>(ldB * lcb);
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dB, sizeof(D) * ldB, b, sizeof(D) * db.ld, sizeof(D) * lrb, lcb, cudaMemcpyHostToDevice, s));
   }
   const std::complex<double> al(*alpha);
@@ -524,8 +525,8 @@ int triangular_solver_host(int ctx, char side, char uplo, char op, char diag, co
   if (lrb > 0 && lcb > 0)
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(b, sizeof(D) * db.ld, dB, sizeof(D) * ldB, sizeof(D) * lrb, lcb, cudaMemcpyDeviceToHost, s));
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(dA);
-  cudaFree(dB);
+  pool_free(dA);
+  pool_free(dB);
   return 0;
 }
 
@@ -589,7 +590,7 @@ int inverse_host(int ctx, int phases, char uplo, char diag, T* a, const DLAF_des
   const long ldA = std::max<long>(lr, 1);
   if (lr > 0 && lc > 0) {
     DLAF_B200_ASSERT(d.ld >= lr, "leading dimension smaller than local rows");
-    DLAF_CUDA_CHECK(cudaMalloc(&dA, sizeof(D) * ldA * lc));
+    dA = pool_alloc<D>(ldA * lc);
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dA, sizeof(D) * ldA, a, sizeof(D) * d.ld, sizeof(D) * lr, lc, cudaMemcpyHostToDevice, s));
   }
   DLAF_descriptor dd = d;
@@ -598,7 +599,7 @@ int inverse_host(int ctx, int phases, char uplo, char diag, T* a, const DLAF_des
   if (lr > 0 && lc > 0)
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(a, sizeof(D) * d.ld, dA, sizeof(D) * ldA, sizeof(D) * lr, lc, cudaMemcpyDeviceToHost, s));
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(dA);
+  pool_free(dA);
   return 0;
 }
 
@@ -674,8 +675,8 @@ int hegst_host(int ctx, char uplo, T* a, const DLAF_descriptor& da, const T* b, 
   const long ld = std::max<long>(lr, 1);
   if (lr > 0 && lc > 0) {
     DLAF_B200_ASSERT(da.ld >= lr && db.ld >= lr, "leading dimension smaller than local rows");
-    DLAF_CUDA_CHECK(cudaMalloc(&dA, sizeof(D) * ld * lc));
-    DLAF_CUDA_CHECK(cudaMalloc(&dB, sizeof(D) * ld * lc));
+    dA = pool_alloc<D>(ld * lc);
+    dB = pool_alloc<D>(ld * lc);
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dA, sizeof(D) * ld, a, sizeof(D) * da.ld, sizeof(D) * lr, lc, cudaMemcpyHostToDevice, s));
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(dB, sizeof(D) * ld, b, sizeof(D) * db.ld, sizeof(D) * lr, lc, cudaMemcpyHostToDevice, s));
   }
@@ -685,8 +686,8 @@ int hegst_host(int ctx, char uplo, T* a, const DLAF_descriptor& da, const T* b, 
   if (lr > 0 && lc > 0)
     DLAF_CUDA_CHECK(cudaMemcpy2DAsync(a, sizeof(D) * da.ld, dA, sizeof(D) * ld, sizeof(D) * lr, lc, cudaMemcpyDeviceToHost, s));
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(dA);
-  cudaFree(dB);
+  pool_free(dA);
+  pool_free(dB);
   return 0;
 }
 
@@ -729,6 +730,7 @@ void dlaf_finalize(void) noexcept {
   if (!g_initialized)
     return;
   g_grids.clear();
+  pool_trim();
   g_initialized = false;
   g_device = -1;
 }
@@ -793,10 +795,12 @@ int dlaf_create_grid(DLAF_Comm comm, int nprow, int npcol, char order) noexcept 
 
 void dlaf_free_grid(int context) noexcept {
   g_grids.erase(context);
+  pool_trim();  // cached workspaces of the solver / inverse / reduction calls (pool.h)
 }
 
 void dlaf_free_all_grids(void) noexcept {
   g_grids.clear();
+  pool_trim();
 }
 
 char grid_ordering(DLAF_Comm comm, int nprow, int npcol, int myprow, int mypcol) noexcept {

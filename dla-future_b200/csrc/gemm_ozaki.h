@@ -48,7 +48,7 @@ struct OzakiSplit {
              int* flag = nullptr, long dst_row0 = 0);
 };
 
-// C = C + alpha * A B^T (alpha = +-1, beta = 1) with A = rows [a_row, a_row + M) of `sa`, B = rows [b_row, b_row + N)
+// C = C + alpha * A B^T (alpha = +-2^e: an exact rescaling of the row scales; beta = 1) with A = rows [a_row, a_row + M) of `sa`, B = rows [b_row, b_row + N)
 // of `sb`; mask / geometry / C taken from `a` (its A, B pointers are ignored). M % 128 == 0, N % 64 == 0,
 // K == kdim <= 512, K % 64 == 0. b_tile_rows: see launch_gemm_tf32x3. guard (device int, may be null): the kernel returns
 // without touching C when *guard != 0 (pair it with launch_gemm_nt_f64_if(..., guard) on the same stream).

@@ -1,6 +1,6 @@
 // fp64 trailing update on tcgen05 via exact int8 digit products (Ozaki scheme), see gemm_ozaki.h.
 //
-//   C(MxN, fp64, column-major) += alpha * A(MxK) B(NxK)^T          alpha = +-1, lower-triangular tile mask
+//   C(MxN, fp64, column-major) += alpha * A(MxK) B(NxK)^T          alpha = +-2^e, lower-triangular tile mask
 //
 // Replaces the cublasDgemm / cublasDsyrk tile calls of the reference's trailing update
 // (include/dlaf/factorization/cholesky/impl.h:69-94, include/dlaf/blas/tile.h:249-304) for the bulk (~95 % of the
@@ -31,6 +31,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
+
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +40,7 @@
 #include "common.h"
 #include "gemm_args.h"
 #include "gemm_ozaki.h"
+#include "pool.h"
 
 namespace dlaf_b200 {
 
@@ -139,7 +142,7 @@ struct OzakiParams {
   double* C;
   long ldc;
   int K;         // int8 k per row (= kdim)
-  double alpha;  // +-1
+  double alpha;  // +-2^e (applied with the power-of-two row scale: exact)
   GemmArgsT<double> g;  // mask / geometry (A, B, C pointers of g are unused here)
   int a_row, b_row;     // row of A(0,:) / B(0,:) inside the split arrays
   int nbp;              // tile edge
@@ -515,8 +518,8 @@ void OzakiSplit::allocate(long rows_max, int kdim_) {
   rows = rows_max;
   kdim = kdim_;
   DLAF_B200_ASSERT(kdim % 128 == 0, "Ozaki split: k must be a multiple of 128");
-  DLAF_CUDA_CHECK(cudaMalloc(&q, static_cast<size_t>(S) * rows * kdim));
-  DLAF_CUDA_CHECK(cudaMalloc(&scale, sizeof(double) * rows));
+  q = pool_alloc<signed char>(static_cast<size_t>(S) * rows * kdim);
+  scale = pool_alloc<double>(rows);
   DLAF_CUDA_CHECK(cudaMemset(q, 0, static_cast<size_t>(S) * rows * kdim));
   // 3-D maps: dim0 = k (contiguous, bytes), dim1 = row, dim2 = digit plane; box = 64 k x {128, BN} rows x 7 planes;
   // 64-byte swizzle
@@ -534,8 +537,8 @@ void OzakiSplit::allocate(long rows_max, int kdim_) {
 }
 
 void OzakiSplit::release() {
-  cudaFree(q);
-  cudaFree(scale);
+  pool_free(q);
+  pool_free(scale);
   q = nullptr;
   scale = nullptr;
 }
@@ -645,7 +648,11 @@ void launch_gemm_ozaki_i8(const GemmArgsT<double>& a, const OzakiSplit& sa, long
     return;
   DLAF_B200_ASSERT(a.M % OBM == 0 && a.N % 64 == 0 && a.K % OBK == 0 && a.K == sa.kdim && a.K == sb.kdim && a.K <= 512,
                    "ozaki gemm shape");
-  DLAF_B200_ASSERT((a.alpha == 1.0 || a.alpha == -1.0) && a.beta == 1.0, "ozaki gemm: C += +-A B^T only");
+  {
+    int ex = 0;
+    const double mant = std::frexp(a.alpha < 0 ? -a.alpha : a.alpha, &ex);
+    DLAF_B200_ASSERT(mant == 0.5 && a.beta == 1.0, "ozaki gemm: C += alpha A B^T with alpha = +-2^e only (exact scaling)");
+  }
   OzakiParams p;
   p.C = a.C;
   p.ldc = a.ldc;

@@ -29,6 +29,7 @@
 #include "common.h"
 #include "gemm_args.h"
 #include "gemm_tf32.h"
+#include "pool.h"
 
 namespace dlaf_b200 {
 
@@ -303,8 +304,8 @@ void Tf32Split::allocate(long rows_max, int kdim_) {
   release();
   rows = rows_max;
   kdim = kdim_;
-  DLAF_CUDA_CHECK(cudaMalloc(&hi, sizeof(float) * rows * kdim));
-  DLAF_CUDA_CHECK(cudaMalloc(&lo, sizeof(float) * rows * kdim));
+  hi = pool_alloc<float>(rows * kdim);
+  lo = pool_alloc<float>(rows * kdim);
   // 2D map: dim0 = k (contiguous), dim1 = row; box = 32 k x 128 rows; 128-byte swizzle
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(kdim), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(kdim) * 4};
@@ -320,8 +321,8 @@ void Tf32Split::allocate(long rows_max, int kdim_) {
 }
 
 void Tf32Split::release() {
-  cudaFree(hi);
-  cudaFree(lo);
+  pool_free(hi);
+  pool_free(lo);
   hi = lo = nullptr;
 }
 

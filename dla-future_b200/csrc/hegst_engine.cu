@@ -7,6 +7,7 @@
 #include "comm.h"
 #include "common.h"
 #include "distribution.h"
+#include "pool.h"
 #include "tri_kernels.cuh"
 
 namespace dlaf_b200 {
@@ -67,8 +68,8 @@ long generalized_to_standard_device(const HegstProblem& p, T* a_user, long lda, 
   const bool have = ltr > 0 && ltc > 0;
   T *sa = nullptr, *sl = nullptr;  // engine slabs of A and L
   if (have) {
-    DLAF_CUDA_CHECK(cudaMalloc(&sa, sizeof(T) * lds * ltc * nbp));
-    DLAF_CUDA_CHECK(cudaMalloc(&sl, sizeof(T) * lds * ltc * nbp));
+    sa = pool_alloc<T>(lds * ltc * nbp);
+    sl = pool_alloc<T>(lds * ltc * nbp);
     DLAF_CUDA_CHECK(cudaMemsetAsync(sa, 0, sizeof(T) * lds * ltc * nbp, s));
     DLAF_CUDA_CHECK(cudaMemsetAsync(sl, 0, sizeof(T) * lds * ltc * nbp, s));
     dim3 grid(nbp / 32, nbp / 32, ltr * ltc), block(32, 8);
@@ -101,7 +102,7 @@ long generalized_to_standard_device(const HegstProblem& p, T* a_user, long lda, 
   const size_t dsz = tsz + wsz;
   T* dloc = nullptr;
   if (!my_diag.empty()) {
-    DLAF_CUDA_CHECK(cudaMalloc(&dloc, sizeof(T) * dsz * my_diag.size()));
+    dloc = pool_alloc<T>(dsz * my_diag.size());
     for (size_t i = 0; i < my_diag.size(); ++i) {
       const int k = my_diag[i];
       pack(sl + static_cast<long>(k / Pe) * nbp + static_cast<long>(k / Qe) * nbp * lds, lds, dloc + dsz * i, nbp, 1, 0, 0, false, false);
@@ -127,16 +128,17 @@ long generalized_to_standard_device(const HegstProblem& p, T* a_user, long lda, 
 
   // ---- workspaces: dbuf = [L_kk | blocks | A_kk (full Hermitian)], two scratch tiles, panel pairs
   T *dbuf = nullptr, *h0 = nullptr, *h1 = nullptr, *pan = nullptr, *panT = nullptr, *rbuf = nullptr;
-  DLAF_CUDA_CHECK(cudaMalloc(&dbuf, sizeof(T) * (2 * tsz + wsz)));
-  DLAF_CUDA_CHECK(cudaMalloc(&h0, sizeof(T) * tsz));
-  DLAF_CUDA_CHECK(cudaMalloc(&h1, sizeof(T) * tsz));
+  dbuf = pool_alloc<T>((2 * tsz + wsz));
+  h0 = pool_alloc<T>(tsz);
+  h1 = pool_alloc<T>(tsz);
   if (!single) {
-    DLAF_CUDA_CHECK(cudaMalloc(&pan, sizeof(T) * 2 * tsz * (ltr > 0 ? ltr : 1)));    // per local row tile: [P(i) | L(i,k)]
-    DLAF_CUDA_CHECK(cudaMalloc(&panT, sizeof(T) * 2 * tsz * (ltc > 0 ? ltc : 1)));   // per local column tile: [P(j) | L(j,k)]
+    pan = pool_alloc<T>(2 * tsz * (ltr > 0 ? ltr : 1));    // per local row tile: [P(i) | L(i,k)]
+    panT = pool_alloc<T>(2 * tsz * (ltc > 0 ? ltc : 1));   // per local column tile: [P(j) | L(j,k)]
   }
-  DLAF_CUDA_CHECK(cudaMalloc(&rbuf, sizeof(T) * tsz * (ltc > 0 ? ltc : 1)));
+  rbuf = pool_alloc<T>(tsz * (ltc > 0 ? ltc : 1));
   BulkUpdate<T> bulk;
   bulk.init(static_cast<long>(ltr) * nbp, static_cast<long>(ltc) * nbp, nbp, 2 * nt, s, 2);
+  bulk.init_extra(nbp, nbp);
 
   // =================================================================================================================
   // phase 1
@@ -166,25 +168,23 @@ long generalized_to_standard_device(const HegstProblem& p, T* a_user, long lda, 
       break;
     T* pcol = have ? sa + static_cast<long>(li1) * nbp + lck * nbp * lds : nullptr;        // A(i > k, k), my rows
     const T* lcol = have ? sl + static_cast<long>(li1) * nbp + lck * nbp * lds : nullptr;  // L(i > k, k)
-    GemmArgsT<T> hm{};  // P -= 1/2 L(i>k,k) A_kk
+    GemmArgsT<T> hm{};  // P -= 1/2 L(i>k,k) A_kk, on the update engine (the factor 1/2 is an exact rescaling)
+    const Operand<T> opLs{lcol, lds, static_cast<long>(nrows) * nbp, 0}, opH{dbuf + dsz, nbp, nbp, 0};
+    bulk.begin_step();
     if (in_col && nrows > 0) {
       launches += solve_rows_against_tile<T>(pcol, lds, static_cast<long>(nrows) * nbp, dbuf, nbp, dbuf + tsz, ns, true, s);
-      hm.A = lcol;
-      hm.lda = lds;
-      hm.B = dbuf + dsz;
-      hm.ldb = nbp;
       hm.C = pcol;
       hm.ldc = lds;
       hm.M = nrows * nbp;
       hm.N = nbp;
       hm.K = nbp;
       hm.alpha = -0.5;
-      hm.beta = 1.0;
       hm.mask = kMaskNone;
       hm.nbp = nbp;
       hm.P = hm.Q = 1;
-      launch_gemm_nt<T>(hm, s);
-      ++launches;
+      launches += bulk.split(false, 1, opLs, nbp, s);  // L(i>k,k): also the A-side operand of the trailing update
+      launches += bulk.split_extra(opH, nbp, s);
+      launches += bulk.gemm_extra(hm, opLs, 1, opH, s);
     }
     // operands of the trailing update
     Operand<T> opP{}, opL{}, opPT{}, opLT{};
@@ -240,9 +240,9 @@ long generalized_to_standard_device(const HegstProblem& p, T* a_user, long lda, 
       g.pcol = ecol;
       g.ti0 = li1;
       g.tj0 = lj1;
-      bulk.begin_step();
       launches += bulk.split(false, 0, opP, nbp, s);
-      launches += bulk.split(false, 1, opL, nbp, s);
+      if (!in_col)
+        launches += bulk.split(false, 1, opL, nbp, s);  // (ranks of the panel's column: done before the first hemm)
       if (!single) {
         launches += bulk.split(true, 0, opPT, nbp, s);
         launches += bulk.split(true, 1, opLT, nbp, s);
@@ -255,10 +255,8 @@ long generalized_to_standard_device(const HegstProblem& p, T* a_user, long lda, 
       }
     }
     // second half of the hemm
-    if (in_col && nrows > 0) {
-      launch_gemm_nt<T>(hm, s);
-      ++launches;
-    }
+    if (in_col && nrows > 0)
+      launches += bulk.gemm_extra(hm, opLs, 1, opH, s);
   }
 
   // =================================================================================================================
@@ -326,15 +324,15 @@ long generalized_to_standard_device(const HegstProblem& p, T* a_user, long lda, 
   if (guard_steps)
     *guard_steps = fired;
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(sa);
-  cudaFree(sl);
-  cudaFree(dloc);
-  cudaFree(dbuf);
-  cudaFree(h0);
-  cudaFree(h1);
-  cudaFree(pan);
-  cudaFree(panT);
-  cudaFree(rbuf);
+  pool_free(sa);
+  pool_free(sl);
+  pool_free(dloc);
+  pool_free(dbuf);
+  pool_free(h0);
+  pool_free(h1);
+  pool_free(pan);
+  pool_free(panT);
+  pool_free(rbuf);
   return launches;
 }
 

@@ -9,6 +9,7 @@
 #include "comm.h"
 #include "common.h"
 #include "distribution.h"
+#include "pool.h"
 #include "bulk_update.cuh"
 #include "tri_kernels.cuh"
 
@@ -55,7 +56,7 @@ long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, nc
   const bool have = ltr > 0 && ltc > 0;
   T* slab = nullptr;
   if (have) {
-    DLAF_CUDA_CHECK(cudaMalloc(&slab, sizeof(T) * lds * ltc * nbp));
+    slab = pool_alloc<T>(lds * ltc * nbp);
     DLAF_CUDA_CHECK(cudaMemsetAsync(slab, 0, sizeof(T) * lds * ltc * nbp, s));
     dim3 grid(nbp / 32, nbp / 32, ltr * ltc), block(32, 8);
     inv_convert_kernel<T, true><<<grid, block, 0, s>>>(a_user, lda, slab, lds, p.n, p.nb, nbp, Pe, Qe, erow, ecol, ltr, transposed,
@@ -77,13 +78,14 @@ long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, nc
 
   // ---- workspaces
   T *colp = nullptr, *panA = nullptr, *panB = nullptr, *dbuf = nullptr, *dloc = nullptr;
-  DLAF_CUDA_CHECK(cudaMalloc(&colp, sizeof(T) * static_cast<size_t>(ltr > 0 ? ltr : 1) * nbp * nbp));
-  DLAF_CUDA_CHECK(cudaMalloc(&panB, sizeof(T) * tsz * (ltc > 0 ? ltc : 1)));
+  colp = pool_alloc<T>(static_cast<size_t>(ltr > 0 ? ltr : 1) * nbp * nbp);
+  panB = pool_alloc<T>(tsz * (ltc > 0 ? ltc : 1));
   if (do_assemble && Qe > 1)
-    DLAF_CUDA_CHECK(cudaMalloc(&panA, sizeof(T) * tsz * (ltr > 0 ? ltr : 1)));
-  DLAF_CUDA_CHECK(cudaMalloc(&dbuf, sizeof(T) * tsz));
+    panA = pool_alloc<T>(tsz * (ltr > 0 ? ltr : 1));
+  dbuf = pool_alloc<T>(tsz);
   BulkUpdate<T> bulk;
-  bulk.init(static_cast<long>(ltr) * nbp, static_cast<long>(ltc) * nbp, nbp, 2 * nt, s);
+  bulk.init(static_cast<long>(ltr) * nbp, static_cast<long>(ltc) * nbp, nbp, 3 * nt + 2, s);
+  bulk.init_extra(nbp, nbp);
 
   // =================================================================================================================
   // (1) W = L^-1
@@ -95,7 +97,7 @@ long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, nc
         my_diag.push_back(k);
     const size_t dsz = 2 * tsz + wsz;
     if (!my_diag.empty()) {
-      DLAF_CUDA_CHECK(cudaMalloc(&dloc, sizeof(T) * dsz * my_diag.size()));
+      dloc = pool_alloc<T>(dsz * my_diag.size());
       for (size_t i = 0; i < my_diag.size(); ++i)
         pack(tile(my_diag[i], my_diag[i]), lds, dloc + dsz * i, nbp, 1, 0, 0, false, false, false);
       static bool configured = false;
@@ -137,24 +139,24 @@ long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, nc
         }
         const long lck = k / Qe;
         if (vrows > 0) {
-          // column panel: W(i,k) = -A(i,k) L_kk^-1 = -A(i,k) Wh_k^H, into the compact panel, then back into the matrix
+          // column panel: W(i,k) = -A(i,k) L_kk^-1 = -A(i,k) Wh_k^H, into the (zeroed) compact panel on the update engine,
+          // then back into the matrix
           GemmArgsT<T> g{};
-          g.A = slab + static_cast<long>(li_k1) * nbp + lck * nbp * lds;
-          g.lda = lds;
-          g.B = whk;
-          g.ldb = nbp;
           g.C = colp + (li_k1 - li_k) * static_cast<long>(nbp);
           g.ldc = mk;
           g.M = static_cast<int>(vrows);
           g.N = nbp;
           g.K = nbp;
           g.alpha = -1.0;
-          g.beta = 0.0;
           g.mask = kMaskNone;
           g.nbp = nbp;
           g.P = g.Q = 1;
-          launch_gemm_nt<T>(g, s);
-          ++launches;
+          DLAF_CUDA_CHECK(cudaMemset2DAsync(g.C, sizeof(T) * mk, 0, sizeof(T) * vrows, nbp, s));
+          const Operand<T> opA{slab + static_cast<long>(li_k1) * nbp + lck * nbp * lds, lds, vrows, 0}, opW{whk, nbp, nbp, 0};
+          bulk.begin_step();
+          launches += bulk.split(false, 0, opA, nbp, s);
+          launches += bulk.split_extra(opW, nbp, s);
+          launches += bulk.gemm_extra(g, opA, 0, opW, s);
           DLAF_CUDA_CHECK(cudaMemcpy2DAsync(slab + static_cast<long>(li_k1) * nbp + lck * nbp * lds, sizeof(T) * lds, g.C,
                                             sizeof(T) * mk, sizeof(T) * vrows, nbp, cudaMemcpyDeviceToDevice, s));
         }
@@ -270,12 +272,12 @@ long inverse_device(const InverseProblem& p, int phases, T* a_user, long lda, nc
   if (guard_steps)
     *guard_steps = fired;
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(slab);
-  cudaFree(colp);
-  cudaFree(panA);
-  cudaFree(panB);
-  cudaFree(dbuf);
-  cudaFree(dloc);
+  pool_free(slab);
+  pool_free(colp);
+  pool_free(panA);
+  pool_free(panB);
+  pool_free(dbuf);
+  pool_free(dloc);
   return launches;
 }
 

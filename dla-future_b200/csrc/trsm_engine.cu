@@ -10,6 +10,7 @@
 #include "common.h"
 #include "distribution.h"
 #include "gemm_ozaki.h"
+#include "pool.h"
 #include "tri_kernels.cuh"
 
 namespace dlaf_b200 {
@@ -130,7 +131,7 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
   T* a_slab = nullptr;
   const long lds = static_cast<long>(ltrA > 0 ? ltrA : 1) * nbp;
   if (ltrA > 0 && ltcA > 0) {
-    DLAF_CUDA_CHECK(cudaMalloc(&a_slab, sizeof(T) * lds * ltcA * nbp));
+    a_slab = pool_alloc<T>(lds * ltcA * nbp);
     dim3 grid(ltrA * ltcA, nbp);
     trsm_load_a_kernel<T><<<grid, 128, 0, s>>>(a_user, lda, a_slab, lds, na, ba, nbp, P, Q, p.prow, p.pcol, ltrA, a_lower, unit);
     DLAF_CUDA_CHECK(cudaGetLastError());
@@ -153,7 +154,7 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
   const int ltcY = cnt(nt, ecol, Qe);
   T* y = nullptr;
   if (ltcY > 0) {
-    DLAF_CUDA_CHECK(cudaMalloc(&y, sizeof(T) * ldy * ltcY * nbp));
+    y = pool_alloc<T>(ldy * ltcY * nbp);
     dim3 grid(static_cast<unsigned>(ltcY * nbp), static_cast<unsigned>((ldy + 1023) / 1024 > 0 ? (ldy + 1023) / 1024 : 1));
     trsm_convert_y_kernel<T, true><<<grid, 256, 0, s>>>(b_user, ldb, lrb, lcb, y, ldy, ba, nbp, left, cre, cim);
     DLAF_CUDA_CHECK(cudaGetLastError());
@@ -167,7 +168,7 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
       my_diag.push_back(k);
   T* dloc = nullptr;
   if (!my_diag.empty()) {
-    DLAF_CUDA_CHECK(cudaMalloc(&dloc, sizeof(T) * (tsz + wsz) * my_diag.size()));
+    dloc = pool_alloc<T>((tsz + wsz) * my_diag.size());
     for (size_t i = 0; i < my_diag.size(); ++i)
       pack(a_tile(my_diag[i], my_diag[i]), dloc + (tsz + wsz) * i, 1, 0, 0);
     dim3 grid(ns, static_cast<unsigned>(my_diag.size()));
@@ -184,12 +185,12 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
   }
   // ---- workspaces of the sweep
   T *dbuf = nullptr, *panelY = nullptr, *panelR = nullptr, *panelG = nullptr;
-  DLAF_CUDA_CHECK(cudaMalloc(&dbuf, sizeof(T) * (tsz + wsz)));
-  DLAF_CUDA_CHECK(cudaMalloc(&panelY, sizeof(T) * ldy * nbp));
+  dbuf = pool_alloc<T>((tsz + wsz));
+  panelY = pool_alloc<T>(ldy * nbp);
   const int ltrR = cnt(nt, erow, Pe);  // tiles t with t % Pe == erow (pattern N: what arrives along my engine row)
   if (pattern_n)
-    DLAF_CUDA_CHECK(cudaMalloc(&panelR, sizeof(T) * tsz * (ltrR > 0 ? ltrR : 1)));
-  DLAF_CUDA_CHECK(cudaMalloc(&panelG, sizeof(T) * tsz * (ltcY > 0 ? ltcY : 1)));
+    panelR = pool_alloc<T>(tsz * (ltrR > 0 ? ltrR : 1));
+  panelG = pool_alloc<T>(tsz * (ltcY > 0 ? ltcY : 1));
 
   // fp64: the per-step update runs on tcgen05 as exact int8 digit products (gemm_ozaki.h), like the POTRF trailing update —
   // Y_k and the G tiles of the step are cut into digit planes first; same guard (a step whose operands span too many
@@ -203,7 +204,7 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
     if (use_oz) {
       oz_a.allocate(ldy, nbp);
       oz_b.allocate(static_cast<long>(pattern_n && Pe == 1 ? (ltrR > 0 ? ltrR : 1) : ltcY) * nbp, nbp);
-      DLAF_CUDA_CHECK(cudaMalloc(&oz_flag, sizeof(int) * nt));
+      oz_flag = pool_alloc<int>(nt);
       DLAF_CUDA_CHECK(cudaMemsetAsync(oz_flag, 0, sizeof(int) * nt, s));
     }
   }
@@ -363,7 +364,7 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
       DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
       oz_a.release();
       oz_b.release();
-      cudaFree(oz_flag);
+      pool_free(oz_flag);
     }
   }
   if (ltcY > 0) {
@@ -373,13 +374,13 @@ long triangular_solve_device(const TrsmProblem& p, double alpha_re, double alpha
     ++launches;
   }
   DLAF_CUDA_CHECK(cudaStreamSynchronize(s));
-  cudaFree(a_slab);
-  cudaFree(y);
-  cudaFree(dloc);
-  cudaFree(dbuf);
-  cudaFree(panelY);
-  cudaFree(panelR);
-  cudaFree(panelG);
+  pool_free(a_slab);
+  pool_free(y);
+  pool_free(dloc);
+  pool_free(dbuf);
+  pool_free(panelY);
+  pool_free(panelR);
+  pool_free(panelG);
   return launches;
 }
 

@@ -85,6 +85,9 @@ def test_eigenvalues_of_the_pencil(pkg, oracle, grid11):
 def test_both_fp64_engines_agree(pkg, oracle, grid11, monkeypatch):
     n, nb = 1536, 256
     a = oracle.set_random_hermitian_positive_definite(n, nb, np.float64)
+    rng = np.random.default_rng(21)
+    m = rng.uniform(-1, 1, (n, n))
+    a = np.asfortranarray(a + (m + m.T))  # (the generator is deterministic: without this A would be equal to B)
     b = oracle.set_random_hermitian_positive_definite(n, nb, np.float64)
     f = b.copy(order="F")
     assert oracle.cholesky_local("L", f, nb, nthreads=8) == 0
@@ -95,3 +98,20 @@ def test_both_fp64_engines_agree(pkg, oracle, grid11, monkeypatch):
     out2 = a.copy(order="F")
     assert pkg.generalized_to_standard(grid11, "L", out2, f, nb) == 0
     assert np.abs(np.tril(out) - np.tril(out2)).max() < 1e-13 * max(1.0, np.abs(np.tril(out2)).max())
+
+
+def test_identical_pencil_gives_identity_and_trips_the_guard(pkg, oracle, grid11):
+    """A == B: the reduced matrix is the identity up to rounding, i.e. the diagonal tiles hold entries ~1e-16 next to 1 — rows
+    spanning > 40 binades, exactly what the int8-digit guard is for: those steps must fall back to native fp64 and the
+    result must be as accurate as the oracle's."""
+    n, nb = 1536, 256
+    b = oracle.set_random_hermitian_positive_definite(n, nb, np.float64)
+    f = b.copy(order="F")
+    assert oracle.cholesky_local("L", f, nb, nthreads=8) == 0
+    out = b.copy(order="F")
+    assert pkg.generalized_to_standard(grid11, "L", out, f, nb) == 0
+    assert pkg.last_inverse_guard_steps(grid11) > 0
+    ref = b.copy(order="F")
+    oracle.generalized_to_standard("L", ref, f, nb)
+    assert np.abs(np.tril(out) - np.eye(n)).max() < 1e-13
+    assert np.abs(np.tril(out) - np.tril(ref)).max() < 1e-13

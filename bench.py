@@ -54,6 +54,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-check", action="store_true")
     p.add_argument("--no-gpu-reference", action="store_true", help="skip the cuSOLVER Dpotrf timing (tools/cusolver_potrf_ref)")
+    p.add_argument("--next-n", type=int, default=8192, help="size of the short measurements of the algorithms that consume the "
+                   "factor (triangular solver, inverse, generalized -> standard; SURVEY 8f), 0 = skip; 1 GPU only")
     p.add_argument("--cpu-sample-n", type=int, default=0, help="force the CPU sample size")
     return p.parse_args()
 
@@ -259,6 +261,99 @@ def oracle_parity(pkg, ctx, torch, dist, rank, world, P, Q, myrow, mycol, n, nb,
             "tolerance": float(tol), "tolerance_rule": "4 (n+1) c eps, |d| or |d|/max(|e|,|v|) (test_cholesky.cpp:76-77)",
             "unreferenced_triangle_untouched": untouched, "grid_residual_max_diff_over_max_a": res,
             "residual_gate_eps_n": float(np.finfo(dt.type(0).real.dtype).eps * n), "seconds": time.perf_counter() - t0}
+
+
+def next_rows(pkg, ctx, torch, O, n: int, nb: int):
+    """SURVEY 8(f) rows 1-3 in the driver-visible line (1 GPU, fp64): the consumers of the factor through the C ABI at a
+    size that takes a fraction of a second — device time of the whole call (CUDA events inside the library), a residual,
+    and an element-wise oracle verdict at n = 1024 with the reference's tolerances. Never part of the timed POTRF region."""
+    out = {}
+    dt = np.float64
+    b = np.zeros((n, n), dtype=dt, order="F")
+    pkg.set_random_hermitian_positive_definite(ctx, b, n, nb)
+    fac = b.copy(order="F")
+    assert pkg.cholesky_factorization(ctx, "L", fac, nb) == 0
+    d_b = torch.from_numpy(b).cuda()  # (symmetric: row- and column-major coincide)
+    d_fac = torch.from_numpy(np.ascontiguousarray(fac.T)).cuda()  # memory = column-major factor
+    eye = torch.eye(n, dtype=torch.float64, device="cuda")
+    # -- inverse from the Cholesky factor
+    ms = []
+    for _ in range(2):
+        w = d_fac.clone()
+        torch.cuda.synchronize()
+        pkg.inverse_device(ctx, 3, "L", "N", w.data_ptr(), dt, n, nb, n)
+        ms.append(pkg.last_solver_device_ms(ctx))
+    low = torch.tril(w.T)
+    res = ((low + torch.tril(low, -1).T) @ d_b - eye).abs().max().item()
+    out["inverse_from_cholesky_factor"] = {"api": "dlaf_b200_inverse_device_d (dlaf_inverse_from_cholesky_factor_d on device memory)",
+                                           "n": n, "nb": nb, "ms_device": min(ms), "value": 2 * n ** 3 / 3 / (min(ms) * 1e-3) / 1e9,
+                                           "unit": "GFLOP/s", "flops_model": "2 n^3 / 3", "max_abs_invA_A_minus_I": res,
+                                           "guard_fallback_steps": pkg.last_inverse_guard_steps(ctx), "launches": pkg.last_solver_launch_count(ctx)}
+    # -- generalized -> standard: A = B with the diagonal shifted (Hermitian, not a multiple of B)
+    d_a = d_b.clone()
+    d_a.diagonal().sub_(float(n))
+    ms = []
+    for _ in range(2):
+        w = d_a.clone()
+        torch.cuda.synchronize()
+        pkg.generalized_to_standard_device(ctx, "L", w.data_ptr(), d_fac.data_ptr(), dt, n, nb, n)
+        ms.append(pkg.last_solver_device_ms(ctx))
+    low = torch.tril(w.T)
+    lmat = torch.tril(d_fac.T)
+    res = torch.tril(lmat @ (low + torch.tril(low, -1).T) @ lmat.T - d_a).abs().max().item() / d_a.abs().max().item()
+    out["generalized_to_standard"] = {"api": "dlaf_b200_generalized_to_standard_device_d", "n": n, "nb": nb, "ms_device": min(ms),
+                                      "value": float(n) ** 3 / (min(ms) * 1e-3) / 1e9, "unit": "GFLOP/s", "flops_model": "n^3",
+                                      "max_LCLh_minus_A_over_max_A": res, "guard_fallback_steps": pkg.last_inverse_guard_steps(ctx),
+                                      "launches": pkg.last_solver_launch_count(ctx)}
+    del w, low, lmat, d_a, d_b, eye
+    # -- triangular solver (host-buffer entry; the device time of the sweep is reported by the library)
+    nrhs = n // 2
+    rng = np.random.default_rng(1)
+    rhs = np.asfortranarray(rng.uniform(-1, 1, (n, nrhs)))
+    lo = np.asfortranarray(np.tril(fac))
+    ms = []
+    for _ in range(2):
+        x = rhs.copy(order="F")
+        pkg.triangular_solver(ctx, "L", "L", "N", "N", 1.0, lo, x, nb, nb)
+        ms.append(pkg.last_solver_device_ms(ctx))
+    d_l, d_x, d_r = (torch.from_numpy(np.ascontiguousarray(v)).cuda() for v in (lo, x, rhs))
+    res = (d_l @ d_x - d_r).abs().max().item() / (np.abs(x).max() * np.abs(lo).max() * n)
+    out["triangular_solver"] = {"api": "dlaf_b200_triangular_solver_d (Left, Lower, NoTrans; host buffers, device time of the sweep)",
+                                "n": n, "nrhs": nrhs, "nb": nb, "ms_device": min(ms), "value": float(n) * n * nrhs / (min(ms) * 1e-3) / 1e9,
+                                "unit": "GFLOP/s", "flops_model": "n^2 nrhs", "residual_over_n_maxA_maxX": res,
+                                "launches": pkg.last_solver_launch_count(ctx)}
+    del d_l, d_x, d_r, d_fac
+    torch.cuda.empty_cache()
+    # -- element-wise oracle verdicts at n = 1024 (reference tolerances)
+    m, mb = 1024, 256
+    spd = O.set_random_hermitian_positive_definite(m, mb, dt)
+    f = spd.copy(order="F")
+    assert O.cholesky_local("L", f, mb, 8) == 0
+    par = {}
+    ref = f.copy(order="F")
+    O.inverse_from_cholesky_factor("L", ref, mb)
+    got = f.copy(order="F")
+    pkg.inverse_from_cholesky_factor(ctx, "L", got, mb)
+    sc = float(np.abs(np.tril(ref)).max())
+    par["inverse_from_cholesky_factor"] = bool(O.check_near(np.tril(ref) / sc, np.tril(got) / sc, O.inverse_tolerance(m, dt),
+                                                            O.inverse_tolerance(m, dt))[0])
+    a2 = np.asfortranarray(spd - m * np.eye(m))
+    ref = a2.copy(order="F")
+    O.generalized_to_standard("L", ref, f, mb)
+    got = a2.copy(order="F")
+    pkg.generalized_to_standard(ctx, "L", got, f, mb)
+    par["generalized_to_standard"] = bool(O.check_near(np.tril(ref), np.tril(got), 0.0,
+                                                       O.gen_to_std_tolerance(m, dt) * max(1.0, float(np.abs(np.tril(ref)).max())))[0])
+    r2 = np.asfortranarray(rng.uniform(-1, 1, (m, 512)))
+    ref = r2.copy(order="F")
+    lo2 = np.asfortranarray(np.tril(f))
+    O.triangular_solver("L", "L", "N", "N", 1.0, lo2, ref, mb, 128)
+    got = r2.copy(order="F")
+    pkg.triangular_solver(ctx, "L", "L", "N", "N", 1.0, lo2, got, mb, 128)
+    tol = O.triangular_tolerance(m, dt) * max(1.0, float(np.abs(ref).max()))
+    par["triangular_solver"] = bool(O.check_near(ref, got, tol, tol)[0])
+    out["elementwise_vs_oracle_n1024"] = par
+    return out
 
 
 def triangle_bytes(n: int, nb: int, P: int, Q: int, vr: int, vc: int, itemsize: int) -> int:
@@ -587,6 +682,16 @@ def run_ours(args):
         except Exception as e:  # pragma: no cover
             log(f"[bench] cusolver reference skipped: {e}")
 
+    # ---- the algorithms that consume the factor, short, after everything that is timed for POTRF
+    nxt = None
+    if rank == 0 and world == 1 and args.next_n > 0 and args.type == "d" and not args.no_check:
+        try:
+            torch.cuda.empty_cache()
+            nxt = next_rows(pkg, ctx, torch, ge.load_oracle(), args.next_n, nb if nb <= 512 else 512)
+        except Exception as e:  # pragma: no cover
+            log(f"[bench] next rows skipped: {e!r}")
+            nxt = {"skipped": repr(e)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC if (args.type, n, nb) == ("d", 32768, 512) else f"POTRF GFLOP/s ({args.type}, N={n}, nb={nb})",
@@ -611,6 +716,7 @@ def run_ours(args):
             "residual_torch_checker": residual_torch,
             "residual_gate_eps_n": eps * n,
             "oracle_parity": parity,
+            "next_rows": nxt,
             "step_ms": step_ms,
         }
         print(json.dumps(line), flush=True)

@@ -39,7 +39,8 @@ def parse():
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
-    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--impl", default="ours", choices=["ours", "reference", "next-rows"],
+                   help="ours / reference: the two arms of the contract; next-rows: child mode of the `next_rows` block")
     # (--matrix-size / --block-size are the miniapp's names; under torchrun use them: its own parser rejects "--n" as an
     # ambiguous abbreviation of --nnodes / --nproc-per-node even after the script name)
     p.add_argument("--n", "--matrix-size", dest="n", type=int, default=32768, help="matrix size (BASELINE metric: 32768)")
@@ -683,11 +684,15 @@ def run_ours(args):
             log(f"[bench] cusolver reference skipped: {e}")
 
     # ---- the algorithms that consume the factor, short, after everything that is timed for POTRF
+    # Runs in a child process (this script, --impl next-rows): nothing it does can take the POTRF line down.
     nxt = None
     if rank == 0 and world == 1 and args.next_n > 0 and args.type == "d" and not args.no_check:
         try:
             torch.cuda.empty_cache()
-            nxt = next_rows(pkg, ctx, torch, ge.load_oracle(), args.next_n, nb if nb <= 512 else 512)
+            env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "next-rows", "--next-n", str(args.next_n),
+                                "--nb", str(nb if nb <= 512 else 512)], capture_output=True, text=True, timeout=600, env=env)
+            nxt = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:  # pragma: no cover
             log(f"[bench] next rows skipped: {e!r}")
             nxt = {"skipped": repr(e)[:200]}
@@ -725,9 +730,22 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_next_rows(args):
+    import torch
+
+    pkg = ge.load_package()
+    pkg.initialize()
+    ctx = pkg.create_grid(None, 1, 1, "C")
+    out = next_rows(pkg, ctx, torch, ge.load_oracle(), args.next_n, args.nb)
+    print(json.dumps(out), flush=True)
+    pkg.free_grid(ctx)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.impl == "next-rows":
+        run_next_rows(a)
     else:
         run_ours(a)

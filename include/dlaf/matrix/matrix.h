@@ -12,6 +12,7 @@
 
 #include <dlaf/common/index2d.h>
 #include <dlaf/communication/communicator_grid.h>
+#include <dlaf/matrix/distribution.h>
 #include <dlaf_c/b200_ext.h>
 #include <dlaf_c/desc.h>
 
@@ -47,6 +48,23 @@ public:
       internal::check(cudaMallocHost(reinterpret_cast<void**>(&ptr_), bytes), "Matrix allocation");
     owns_ = true;
     internal::check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "stream");
+  }
+  // From a Distribution, as the reference's tests build their matrices (test/unit/factorization/test_cholesky.cpp:87-88:
+  // `Distribution distribution(size, block_size, grid.size(), grid.rank(), src_rank_index); Matrix<T, D> mat(std::move(distribution));`).
+  // The reference's constructor needs no grid because its communicators travel separately; here the matrix is bound to the
+  // grid context, so the grid is the second argument (it must be the grid the distribution was built from).
+  Matrix(const matrix::Distribution& distribution, comm::CommunicatorGrid& grid)
+      : Matrix(distribution.size(), distribution.tile_size(), grid, distribution.source_rank_index()) {
+    if (!(distribution.grid_size() == grid.size()) || !(distribution.rank_index() == grid.rank())) {
+      std::fprintf(stderr, "[dlaf] Matrix: the distribution does not belong to the given communicator grid\n");
+      std::abort();
+    }
+  }
+  // the bookkeeping of this matrix (reference: Matrix::distribution(), matrix_base.h)
+  matrix::Distribution distribution() const {
+    int v[4];
+    dlaf_b200_grid_info(ctx_, v);
+    return matrix::Distribution(size_, block_, grid_size_, comm::Index2D(v[2], v[3]), src_rank_);
   }
   // Wraps caller memory: local part at `ptr`, column-major with leading dimension `ld`.
   Matrix(GlobalElementSize size, TileElementSize block, comm::CommunicatorGrid& grid, comm::Index2D src_rank,

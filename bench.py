@@ -291,7 +291,7 @@ def next_rows(pkg, ctx, torch, O, n: int, nb: int):
                                            "unit": "GFLOP/s", "flops_model": "2 n^3 / 3", "max_abs_invA_A_minus_I": res,
                                            "guard_fallback_steps": pkg.last_inverse_guard_steps(ctx), "launches": pkg.last_solver_launch_count(ctx)}
     # -- generalized -> standard: A = B with the diagonal shifted (Hermitian, not a multiple of B)
-    d_a = d_b.clone()
+    d_a = d_b.contiguous().clone()  # row-major copy of a symmetric matrix: its memory is also the column-major matrix
     d_a.diagonal().sub_(float(n))
     ms = []
     for _ in range(2):

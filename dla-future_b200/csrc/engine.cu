@@ -112,12 +112,16 @@ PotrfEngine<T>::PotrfEngine(const EngineGeometry& g, ncclComm_t row_comm, ncclCo
       for (int k = 0; k < nt_; ++k)
         h_oz_flags_[k] = 0;
     }
-    if (use_ozaki_)
-      for (int i = 0; i < 2; ++i) {
+    if (use_ozaki_) {
+      oring_ = (geo_.P * geo_.Q == 1) ? kOzRing : 2;
+      if (const char* r = std::getenv("DLAF_B200_OZAKI_RING"))
+        oring_ = (geo_.P * geo_.Q == 1) ? std::min(kOzRing, std::max(2, std::atoi(r))) : 2;
+      for (int i = 0; i < oring_; ++i)
         osplit_[i].allocate(static_cast<long>(ltr_) * nbp_, nbp_);
-        if (geo_.P > 1)
+      if (geo_.P > 1)
+        for (int i = 0; i < 2; ++i)
           osplitT_[i].allocate(static_cast<long>(ltc_) * nbp_, nbp_);
-      }
+    }
   }
   if constexpr (std::is_same_v<T, float>) {
     // DLAF_B200_S_SIMT=1 keeps the SIMT fp32 kernel everywhere (A/B measurements)
@@ -179,10 +183,10 @@ PotrfEngine<T>::~PotrfEngine() {
     }
   }
   if constexpr (std::is_same_v<T, double>) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kOzRing; ++i)
       osplit_[i].release();
+    for (int i = 0; i < 2; ++i)
       osplitT_[i].release();
-    }
   }
   cudaFree(oz_flag_);
   cudaFreeHost(h_oz_flags_);
@@ -499,11 +503,11 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       if (mt > 1)
         trsm_panel(tile_ptr(li1 + 1, lkc), ld_, (mt - 1) * nbp_, tkk, ldt, w, sR_);
       if (k < nt_ - 1) {
-        if (k >= 2)  // the digit planes of this slot were last read by the updates of step k-2
-          wait_bulk(k - 2, -1, sR_);
+        if (k >= oring_)  // the digit planes of this ring slot were last read by the updates of step k - oring_
+          wait_bulk(k - oring_, -1, sR_);
         DLAF_CUDA_CHECK(cudaStreamWaitEvent(sR_, evT1_[slot], 0));
         if constexpr (std::is_same_v<T, double>) {
-          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sR_, 0, 0, oz_flag_ + k);
+          osplit_[k % oring_].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sR_, 0, 0, oz_flag_ + k);
           ++launches_;
         }
       }
@@ -525,7 +529,9 @@ void PotrfEngine<T>::panel_step(int k, bool wait_column) {
       }
       if constexpr (std::is_same_v<T, double>) {
         if (use_ozaki_ && k < nt_ - 1 && P * Q == 1) {
-          osplit_[slot].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sH_, 0, 0, oz_flag_ + k);
+          if (k >= oring_)  // ring slot last read by the updates of step k - oring_ (all column chunks)
+            wait_bulk(k - oring_, -1, sH_);
+          osplit_[k % oring_].split(tile_ptr(li1, lkc), ld_, static_cast<long>(mt) * nbp_, sH_, 0, 0, oz_flag_ + k);
           ++launches_;
         }
       }
@@ -900,7 +906,7 @@ void PotrfEngine<T>::launch_update(int k, int cj0, int ncols, int ri0, int mrows
       if (P > 1)
         launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplitT_[slot], static_cast<long>(cj0 - lj1) * nbp_, st, 0, guard);
       else
-        launch_gemm_ozaki_i8(a, osplit_[slot], a_row, osplit_[slot], static_cast<long>(gj0 - (k + 1)) * nbp_, st,
+        launch_gemm_ozaki_i8(a, osplit_[k % oring_], a_row, osplit_[k % oring_], static_cast<long>(gj0 - (k + 1)) * nbp_, st,
                              static_cast<long>(Q) * nbp_, guard);
       // guard raised by the digit split of this step's panel: the same update on the native fp64 kernel (otherwise
       // a handful of CTAs that read the flag and leave)
@@ -987,13 +993,17 @@ int PotrfEngine<T>::chunk_of(int lj) const {
 template <class T>
 void PotrfEngine<T>::wait_bulk(int k, int lj, cudaStream_t st) {
   const int nc = nchunks();
-  if (geo_.P * geo_.Q > 1 || lj < 0 || split_panels()) {
-    // distributed / split panels: the panel workspaces of step k are shared by all chunks -> wait for all
+  // lj < 0: a workspace of step k is about to be reused -> every chunk must be done with it. lj >= 0: data dependency on
+  // one block column -> its chunk is enough, unless the panel workspaces of step k + 2 are about to overwrite what the
+  // other chunks still read (grids, fp32 splits: two slots; the int8 digit planes on a 1 x 1 grid live in a ring and
+  // are protected separately, see panel_step).
+  const bool ring = use_ozaki_ && geo_.P * geo_.Q == 1 && oring_ > 2;
+  if (geo_.P * geo_.Q > 1 || lj < 0 || (split_panels() && !ring)) {
     for (int c = 0; c < nc; ++c)
-      DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[2 * c + k % 2], 0));
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[oring_ * c + k % oring_], 0));
   }
   else {
-    DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[2 * chunk_of(lj) + k % 2], 0));
+    DLAF_CUDA_CHECK(cudaStreamWaitEvent(st, evBc_[oring_ * chunk_of(lj) + k % oring_], 0));
   }
 }
 
@@ -1149,6 +1159,14 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sIn_, ev_start_, 0));
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sOut_, ev_start_, 0));
     issue_uploads();
+    // Downloads have slack (a block column is final long before the end), uploads do not (every step needs the whole
+    // trailing matrix): keep the link for the upload first. DLAF_B200_HOST_DEFER_D2H=0 lets both directions compete.
+    static const bool defer = [] {
+      const char* e = std::getenv("DLAF_B200_HOST_DEFER_D2H");
+      return e == nullptr || std::atoi(e) != 0;
+    }();
+    if (defer && !evIn_.empty() && !in_end_.empty())
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(sOut_, evIn_[in_end_.size() - 1], 0));
   }
   else {
     // device-resident: column chunks of equal width (DLAF_B200_BULK_CHUNKS, default 1 = one bulk launch per step)
@@ -1170,7 +1188,7 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
     DLAF_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     sLc_.push_back(make_bulk_stream(least, geo_.P * geo_.Q));
   }
-  while (static_cast<int>(evBc_.size()) < 2 * nc) {
+  while (static_cast<int>(evBc_.size()) < oring_ * nc) {
     cudaEvent_t e;
     DLAF_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     evBc_.push_back(e);
@@ -1219,7 +1237,7 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
         prof_flops_[prof_used_] = (launches_ > before) ? last_update_flops_ : -1.0;
         ++prof_used_;
       }
-      DLAF_CUDA_CHECK(cudaEventRecord(evBc_[2 * c + k % 2], st));
+      DLAF_CUDA_CHECK(cudaEventRecord(evBc_[oring_ * c + k % oring_], st));
     }
     // stream M: block column k+1 below its diagonal tile (needs panel k and the bulk of step k-1 there)
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(sM_, (dist_split_ && use_ozaki_) ? evPc_[k % 2] : evP_[k % 2], 0));
@@ -1254,7 +1272,7 @@ void PotrfEngine<T>::factorize(cudaStream_t s) {
   DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evP_[(nt_ - 1) % 2], 0));
   if (nt_ >= 2) {
     for (int c = 0; c < nc; ++c)
-      DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evBc_[2 * c + (nt_ - 2) % 2], 0));
+      DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evBc_[oring_ * c + (nt_ - 2) % oring_], 0));
     DLAF_CUDA_CHECK(cudaStreamWaitEvent(s, evC_[(nt_ - 2) % 2], 0));
   }
   DLAF_CUDA_CHECK(cudaMemcpyAsync(h_info_, d_info_, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -169,7 +169,7 @@ private:
   // only depends on its own history, so updates of early chunks proceed while later ones are still being
   // uploaded. Device-resident runs use a single chunk.
   std::vector<cudaStream_t> sLc_;
-  std::vector<cudaEvent_t> evBc_;  // [2*c + parity]
+  std::vector<cudaEvent_t> evBc_;  // [oring_ * c + k % oring_]
   int chunk_of(int lj) const;
   int nchunks() const { return in_end_.empty() ? 1 : static_cast<int>(in_end_.size()); }
   void wait_bulk(int k, int lj, cudaStream_t st);  // bulk of step k done on the chunk of column lj (or on all)
@@ -180,7 +180,13 @@ private:
   Tf32Split splitT_[2];  // transposed panel (P > 1 only: tiles (j,k) for my local columns j)
   // fp64 only: tcgen05 int8 Ozaki-scheme trailing update (gemm_ozaki_i8.cu) — same life cycle as the TF32 splits
   bool use_ozaki_ = false;
-  OzakiSplit osplit_[2];
+  // 1 x 1 grid: a RING of kOzRing digit-plane slots instead of two, so that the panel chain may run that many steps ahead
+  // of the slowest column chunk — in the host path the chunks that are still being uploaded — instead of stalling at
+  // step 2 until the whole matrix has arrived (the planes are the only per-step workspace the lagging bulk updates read;
+  // the fp64 panel itself is the final block column of the matrix).
+  static constexpr int kOzRing = 16;
+  int oring_ = 2;  // slots in use: kOzRing on a 1 x 1 grid with the int8 engine, else 2 (like every other workspace)
+  OzakiSplit osplit_[kOzRing];
   OzakiSplit osplitT_[2];
   // guard of the int8 engine (gemm_ozaki.h): one device flag per step, raised by the digit split of that step's panel
   // when a row spans too many binades; the updates of a flagged step run on the native fp64 kernel instead

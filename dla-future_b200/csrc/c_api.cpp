@@ -240,6 +240,7 @@ EngineSlot<devtype_t<T>>& get_engine(GridCtx& c, const DLAF_descriptor& d, const
   key.transposed = upper ? 1 : 0;
   if (!slot.eng || !(slot.key == key)) {
     slot.eng.reset();
+    pool_trim();  // a new engine allocates its slab and workspaces with plain cudaMalloc: give the cached blocks back first
     EngineGeometry g;
     g.n = u.n;
     g.nb = u.nb;

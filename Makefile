@@ -55,6 +55,7 @@ miniapp/miniapp_cholesky: miniapp/miniapp_cholesky.cpp $(LIB) $(wildcard include
 	g++ $(CXXFLAGS) $< -o $@ -L$(LIBDIR) -ldlaf_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../$(LIBDIR)' -Wl,-rpath,/usr/local/cuda/lib64 -lpthread
 
 clean:
-	rm -rf build tools/gpu_diag_tile_test tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref $(LIBDIR)/*.so
+	rm -rf build tools/gpu_diag_tile_test tools/gpu_kernel_test tools/gpu_chain_test tools/gpu_ozaki_test tools/cusolver_potrf_ref \
+	       tools/cublas_tile_potrf_ref tools/cusolvermg_potrf_ref miniapp/miniapp_cholesky $(LIBDIR)/*.so
 
 .PHONY: all clean

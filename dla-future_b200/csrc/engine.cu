@@ -1010,8 +1010,14 @@ void PotrfEngine<T>::wait_bulk(int k, int lj, cudaStream_t st) {
 template <class T>
 void PotrfEngine<T>::issue_uploads() {
   // one 2D copy per local block column (rows from its diagonal tile down), grouped into chunks of
-  // ~256 MB; an event per chunk. The copy stream is in order, so chunk c resident => chunks < c resident.
-  const size_t chunk_bytes = size_t(256) << 20;
+  // ~1 GB (DLAF_B200_UPLOAD_CHUNK_MB; measured at N = 32768: 128 / 256 / 512 MB chunks 228 / 220 / 228 ms end to end,
+  // 1024 MB 197 ms — every chunk costs one bulk launch per step, and narrow launches re-read the panel); an event per chunk. The copy stream is in order, so chunk c resident => chunks < c resident.
+  static const size_t chunk_mb = [] {
+    const char* e = std::getenv("DLAF_B200_UPLOAD_CHUNK_MB");
+    const long v = e ? std::atol(e) : 1024;
+    return static_cast<size_t>(v < 16 ? 16 : v);
+  }();
+  const size_t chunk_bytes = chunk_mb << 20;
   const int nb = geo_.nb;
   in_end_.clear();
   size_t acc = 0, used = 0;
